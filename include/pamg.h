@@ -1,0 +1,201 @@
+/* pamg.h — C ABI of the B200-native AMG-PCG solve phase (libpamg.so).
+ *
+ * This is the drop-in boundary for the path tirtho109/parallel_AMG applies through
+ * PartitionedArrays.jl.  The reference snapshot defines NO interface of its own
+ * (/root/reference/README.md:1-2 is the whole repository), so every entry point below cites
+ * the PartitionedArrays.jl / PartitionedSolvers.jl call it stands in for as recalled in
+ * SURVEY.md Appendix A [RECALL-UNVERIFIED]; the Julia `ccall` stubs are in julia/PAMG.jl and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every host array, the library copies on
+ *     entry and never retains a host pointer; the library owns all device memory.
+ *   - every function returns PAMG_OK (0) or a negative pamg_status; nothing throws or aborts
+ *     across the ABI; pamg_last_error() gives the CUDA / argument error text.
+ *   - ids are 0-based (the Julia shim subtracts 1); global ids int64, local ids int32.
+ *   - local order of a part = own ids (ascending global id) then ghost ids (ascending
+ *     (owner part, global id)).
+ *   - vectors cross the ABI as `nparts` host pointers to OWN values (n_own doubles each);
+ *     entries for parts that are not device-resident in this process may be NULL.
+ *   - not thread-safe per context; distinct contexts are independent.
+ */
+#ifndef PAMG_H
+#define PAMG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pamg_ctx pamg_ctx;
+
+typedef enum {
+  PAMG_OK = 0,
+  PAMG_ERR_ARG = -1,      /* bad argument / call order */
+  PAMG_ERR_CUDA = -2,     /* CUDA runtime error (text in pamg_last_error) */
+  PAMG_ERR_NOGPU = -3,    /* no usable CUDA device: there is NO CPU fallback */
+  PAMG_ERR_COMM = -4,     /* peer mapping / halo time-out */
+  PAMG_ERR_NOTCONV = -5,  /* pcg hit maxiter (x still holds the last iterate) */
+  PAMG_ERR_ALLOC = -6
+} pamg_status;
+
+enum { PAMG_SMOOTHER_JACOBI = 0, PAMG_SMOOTHER_L1JACOBI = 1, PAMG_SMOOTHER_CHEBYSHEV = 2 };
+enum { PAMG_FORMAT_AUTO = 0, PAMG_FORMAT_CSR = 1, PAMG_FORMAT_SELL = 2 };
+/* blocks of the split (own/ghost) storage of a level, PSparseMatrix own_own_values /
+ * own_ghost_values (SURVEY.md App. A "PSparseMatrix") */
+enum { PAMG_A_OO = 0, PAMG_A_OG = 1, PAMG_P_OO = 2, PAMG_P_OG = 3, PAMG_R_OO = 4, PAMG_R_OG = 5 };
+
+/* PartitionedSolvers `amg(; fine_params, coarse_params)` keyword set (App. A) + kernel knobs */
+typedef struct {
+  int32_t struct_size;    /* = sizeof(pamg_options), checked */
+  double eps_strength;    /* smoothed_aggregation(; epsilon): 0 => structural strength */
+  int32_t coarse_size;    /* amg_coarse_params(; coarse_size) */
+  int32_t max_levels;     /* amg_fine_params(; n_fine_levels)+1 */
+  int32_t smoother;       /* PAMG_SMOOTHER_* : jacobi(; iters, omega) / l1 / chebyshev */
+  double omega_jacobi;    /* jacobi(; omega) */
+  int32_t nu_pre;         /* pre_smoother iters */
+  int32_t nu_post;        /* pos_smoother iters */
+  int32_t cheb_degree;
+  double cheb_lo_frac;    /* Chebyshev interval [lo_frac*rho, hi_frac*rho] of D^-1 A */
+  double cheb_hi_frac;
+  int32_t spmv_format;    /* PAMG_FORMAT_* ; AUTO picks per level from the nnz/row histogram */
+  int32_t use_graph;      /* 1: replay the V-cycle / PCG iteration as CUDA graphs */
+  int32_t lanes_per_row;  /* 0: auto (from mean nnz/row); else 1,2,4,8,16,32 for CSR */
+  int32_t tail_rows;      /* levels whose global rows <= this run inside one fused tail kernel (0: off) */
+} pamg_options;
+
+typedef struct {
+  int64_t n_global;       /* rows of A_level over all parts */
+  int64_t n_own, n_ghost; /* this part */
+  int64_t n_own_coarse;   /* own rows of the next level (0 on the coarsest) */
+  int64_t nnz[6];         /* PAMG_A_OO .. PAMG_R_OG */
+  int32_t n_recv_nbrs, n_send_nbrs;
+  int64_t n_send;         /* total entries of the send lists */
+  double rho;             /* Gershgorin bound of rho(D^-1 A) on this level */
+  double omega_p;         /* prolongator smoothing weight 4/(3 rho_F) (0 on the coarsest) */
+} pamg_level_info;
+
+typedef struct {
+  int32_t iters;
+  int32_t converged;
+  double r0_norm, r_norm;
+  double solve_ms;        /* device time of the last pamg_pcg (CUDA events, max over local parts) */
+  double vcycle_ms;       /* device time of the last pamg_vcycle */
+  int64_t kernel_launches;/* kernels launched (or graph kernel nodes replayed) by the last call */
+  int32_t n_levels;
+  int32_t format[16];     /* PAMG_FORMAT_* chosen per level for A */
+  int32_t lanes[16];      /* lanes per row chosen per level for A (CSR) */
+} pamg_stats;
+
+void pamg_default_options(pamg_options* o);
+
+/* ---- context ---------------------------------------------------------------------------
+ * nparts = length of the PartitionedArrays `ranks` array (`distribute(LinearIndices((np,)))`). */
+int pamg_create(int32_t nparts, pamg_ctx** out);
+void pamg_destroy(pamg_ctx* c);
+const char* pamg_last_error(const pamg_ctx* c);
+
+/* ---- problem input (host) --------------------------------------------------------------
+ * pamg_set_part_rows: one call per part = the assembled rows of a PSparseMatrix held by that
+ * part (`psparse(I,J,V,rows,cols) |> fetch`, own rows, GLOBAL column ids), CSR by own row in
+ * own_to_global order.  Julia's SparseMatrixCSC of a symmetric A is a valid CSR of A. */
+int pamg_set_part_rows(pamg_ctx* c, int32_t part, int64_t n_own, const int64_t* own_to_global,
+                       const int64_t* rowptr, const int64_t* col_gid, const double* val);
+/* whole matrix + owner[gid] (one call; equivalent to nparts pamg_set_part_rows calls) */
+int pamg_set_matrix_global(pamg_ctx* c, int64_t n, const int64_t* rowptr, const int64_t* col,
+                           const double* val, const int32_t* owner);
+/* gallery (PartitionedArrays `laplacian_fdm(nodes_per_dir, parts_per_dir, ranks)`) with
+ * `uniform_partition(ranks, parts_per_dir, nodes_per_dir)` ownership */
+int pamg_gallery_poisson(pamg_ctx* c, int32_t ndim, const int64_t* nodes_per_dir,
+                         const int32_t* parts_per_dir);
+/* -div(K grad u), K = diag(k,k,eps_z k), k in {1,kmax} on a blocks^d checkerboard (config 5) */
+int pamg_gallery_diffusion_jump(pamg_ctx* c, int32_t ndim, const int64_t* nodes_per_dir,
+                                const int32_t* parts_per_dir, int32_t blocks, double kmax,
+                                double eps_z);
+int pamg_uniform_partition(int32_t ndim, const int64_t* nodes_per_dir,
+                           const int32_t* parts_per_dir, int32_t* owner_out);
+/* y = A x on the global host matrix (builds right-hand sides b = A*1 without a second copy) */
+int pamg_host_matvec_global(pamg_ctx* c, const double* x, double* y);
+int pamg_global_size(pamg_ctx* c, int64_t* n, int64_t* nnz);
+
+/* ---- AMG setup on the host (PartitionedSolvers `setup(amg(...), x, A, b)`) ------------- */
+int pamg_setup(pamg_ctx* c, const pamg_options* o);
+/* external hierarchy (built by the caller, e.g. PartitionedSolvers itself), level by level,
+ * part by part, in the split format; any block pointer triple may be NULL when empty */
+int pamg_hierarchy_begin(pamg_ctx* c, int32_t n_levels, const pamg_options* o);
+int pamg_level_upload(pamg_ctx* c, int32_t level, int32_t part, int64_t n_own, int64_t n_ghost,
+                      const int64_t* own_to_global, const int64_t* ghost_to_global,
+                      const int32_t* ghost_to_owner, int64_t n_own_coarse, int64_t n_ghost_coarse,
+                      const int64_t* const rowptr[6], const int32_t* const col[6],
+                      const double* const val[6], double rho);
+int pamg_coarse_upload(pamg_ctx* c, int64_t n, const double* inverse_row_major);
+int pamg_hierarchy_end(pamg_ctx* c);
+
+/* ---- hierarchy queries (bit-exact parity of maps / aggregates / CSR structure) --------- */
+int pamg_num_levels(pamg_ctx* c, int32_t* n_levels);
+int pamg_get_level_info(pamg_ctx* c, int32_t level, int32_t part, pamg_level_info* info);
+int pamg_get_index_maps(pamg_ctx* c, int32_t level, int32_t part, int64_t* own_to_global,
+                        int64_t* ghost_to_global, int32_t* ghost_to_owner);
+int pamg_get_block(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int64_t* rowptr,
+                   int32_t* col, double* val);
+int pamg_get_aggregates(pamg_ctx* c, int32_t level, int32_t part, int32_t* agg_local);
+/* nbr_part/slot0/count have n_*_nbrs entries; send_idx has n_send entries (own local ids,
+ * concatenated per neighbour in nbr order) */
+int pamg_get_halo_plan(pamg_ctx* c, int32_t level, int32_t part, int32_t* recv_part,
+                       int32_t* recv_slot0, int32_t* recv_count, int32_t* send_part,
+                       int32_t* send_slot0, int32_t* send_count, int32_t* send_idx);
+int pamg_get_coarse_inverse(pamg_ctx* c, int64_t* n, double* inverse_row_major /* may be NULL */);
+int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double* diag_l1);
+
+/* ---- device residency ------------------------------------------------------------------
+ * Upload the parts this process drives.  One part per GPU is the production layout; several
+ * parts may share one device (PartitionedArrays "debug backend" on one GPU).  With
+ * nlocal < nparts the remaining parts live in other processes (one process per GPU) and
+ * are wired up through the export/import/connect calls: the caller all-gathers the opaque
+ * handle blobs (torch.distributed / MPI.Allgather), nothing else crosses processes on the host. */
+int pamg_device_init(pamg_ctx* c, int32_t nlocal, const int32_t* local_parts,
+                     const int32_t* device_ids);
+int32_t pamg_comm_handle_bytes(void);
+int pamg_comm_export(pamg_ctx* c, int32_t local_part, void* blob);
+int pamg_comm_import(pamg_ctx* c, int32_t remote_part, const void* blob);
+int pamg_comm_connect(pamg_ctx* c);
+
+/* ---- operators on device-resident levels (host vectors in, host vectors out) -----------
+ * x, y: arrays of nparts pointers to own values of the level's row partition. */
+int pamg_spmv(pamg_ctx* c, int32_t level, const double* const* x, double* const* y); /* mul!(y,A,x) */
+/* v: nparts pointers to LOCAL values (own then ghost); ghosts are overwritten */
+int pamg_consistent(pamg_ctx* c, int32_t level, double* const* v);                  /* consistent!(v) |> wait */
+/* owners += ghost copies (ascending neighbour part, ascending slot), ghosts <- 0 */
+int pamg_assemble(pamg_ctx* c, int32_t level, double* const* v);                    /* assemble!(v) |> wait */
+/* x <- nu sweeps of the configured smoother on A_level x = b (x is in/out) */
+int pamg_smooth(pamg_ctx* c, int32_t level, int32_t nu, const double* const* b, double* const* x);
+/* bc = R (b - A x)  (fused residual + restriction); r (may be NULL) receives b - A x */
+int pamg_residual_restrict(pamg_ctx* c, int32_t level, const double* const* b,
+                           const double* const* x, double* const* r, double* const* bc);
+/* x += P ec (fused prolongation + correction) */
+int pamg_prolong_correct(pamg_ctx* c, int32_t level, const double* const* ec, double* const* x);
+int pamg_dot(pamg_ctx* c, int32_t level, const double* const* u, const double* const* v, double* out);
+/* x = V-cycle(b) from x = 0 (the preconditioner apply, `ldiv!(x, P, b)` / `solve!(x,S,b)`) */
+int pamg_vcycle(pamg_ctx* c, const double* const* b, double* const* x);
+/* AMG-preconditioned CG from x = 0 to ||r|| <= rtol ||r0||.  resid_hist (may be NULL) gets
+ * hist[0]=||r0||, hist[k]=||r_k||, capacity maxiter+1.  precond=0 runs plain CG. */
+int pamg_pcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter,
+             int32_t precond, int32_t* iters, double* resid_hist);
+
+/* ---- device-resident benchmarking hooks (inputs already in HBM) ------------------------
+ * pamg_load_rhs copies b to the device once; pamg_pcg_resident re-solves from x=0 with the
+ * resident b and leaves x on the device (pamg_read_solution fetches it). */
+int pamg_load_rhs(pamg_ctx* c, const double* const* b);
+int pamg_pcg_resident(pamg_ctx* c, double rtol, int32_t maxiter, int32_t precond, int32_t* iters,
+                      double* resid_hist);
+int pamg_read_solution(pamg_ctx* c, double* const* x);
+/* time `reps` launches of one level-`level` kernel with CUDA events on the launching stream,
+ * L2 flushed before each when flush_l2 != 0.  kind: 0 spmv, 1 smoother sweep,
+ * 2 residual+restrict, 3 prolong+correct, 4 dot, 5 whole V-cycle.  ms_out[reps]. */
+int pamg_time_kernel(pamg_ctx* c, int32_t kind, int32_t level, int32_t reps, int32_t flush_l2,
+                     float* ms_out);
+int pamg_get_stats(pamg_ctx* c, pamg_stats* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAMG_H */

@@ -1,0 +1,1464 @@
+// engine.cu — device-resident hierarchy, halo/all-reduce wiring over peer memory, V-cycle and
+// PCG schedules (CUDA graphs), behind the C ABI of include/pamg.h.
+//
+// Layout in HBM, per (level, part): split CSR blocks A_oo / A_og, P_oo / P_og, R_oo / R_og
+// (fp64 values, int32 local columns, int32 row pointers; own-ghost blocks stored as a compressed
+// list of boundary rows), smoother weights, and own-length work vectors.  Ghost values never
+// live in the vectors: they arrive in a per-level, double-buffered staging area inside the
+// part's peer-visible "arena", written directly by the neighbouring GPUs.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+#include "kernels.cuh"
+
+namespace pamg {
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      throw CudaError(std::string(#call) + " -> " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                      std::to_string(__LINE__) + ")");                                                \
+  } while (0)
+
+namespace {
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() {
+    if (p) cudaFree(p);
+  }
+  void alloc(size_t count, bool zero = true) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = count;
+    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) CK(cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  void upload(const T* h, size_t count) {
+    alloc(count, false);
+    if (count) CK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void upload(const std::vector<T>& v) { upload(v.data(), v.size()); }
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct DevCsr {
+  DBuf<int32_t> ptr, col, rows;
+  DBuf<double> val;
+  int32_t nrows = 0;   // logical rows (compressed list length when `listed`)
+  bool listed = false;
+  int64_t nnz = 0;
+  int lanes = 8;
+  CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
+};
+
+int pick_lanes(double mean) {
+  if (mean <= 1.5) return 1;
+  if (mean <= 3.0) return 2;
+  if (mean <= 6.0) return 4;
+  if (mean <= 12.0) return 8;
+  if (mean <= 24.0) return 16;
+  return 32;
+}
+
+void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override) {
+  const int64_t nr = m.nrows;
+  std::vector<int32_t> ptr;
+  d.listed = compress;
+  d.nnz = m.nnz();
+  if (m.ptr.empty()) {  // absent block
+    d.nrows = compress ? 0 : (int32_t)nr;
+    ptr.assign((compress ? 0 : nr) + 1, 0);
+    d.ptr.upload(ptr);
+    d.col.alloc(0);
+    d.val.alloc(0);
+    d.rows.alloc(0);
+    return;
+  }
+  if (compress) {
+    std::vector<int32_t> rows;
+    ptr.push_back(0);
+    for (int64_t i = 0; i < nr; ++i)
+      if (m.ptr[i + 1] > m.ptr[i]) {
+        rows.push_back((int32_t)i);
+        ptr.push_back((int32_t)m.ptr[i + 1]);
+      }
+    d.nrows = (int32_t)rows.size();
+    d.rows.upload(rows);
+  } else {
+    ptr.resize(nr + 1);
+    for (int64_t i = 0; i <= nr; ++i) ptr[i] = (int32_t)m.ptr[i];
+    d.nrows = (int32_t)nr;
+    d.rows.alloc(0);
+  }
+  d.ptr.upload(ptr);
+  d.col.upload(m.col);
+  d.val.upload(m.val);
+  const double mean = d.nrows ? (double)d.nnz / d.nrows : 0.0;
+  d.lanes = lanes_override > 0 ? lanes_override : pick_lanes(mean);
+}
+
+// byte offsets inside a part's peer-visible arena; computable by every process for every part
+struct ArenaLayout {
+  std::vector<size_t> ghost, flags, asm_stage, asm_flags;
+  size_t coarse = 0, coarse_flags = 0, red = 0, red_flags = 0, total = 0;
+};
+
+ArenaLayout arena_layout(const Hierarchy& h, int part) {
+  ArenaLayout a;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + std::max<size_t>(bytes, 8), 256);
+    return o;
+  };
+  for (const Level& lev : h.levels) {
+    const PartLevel& pl = lev.parts[part];
+    a.ghost.push_back(take(2 * (size_t)pl.n_ghost * sizeof(double)));
+    a.flags.push_back(take(pl.recv.size() * sizeof(uint32_t)));
+    a.asm_stage.push_back(take(pl.send_idx.size() * sizeof(double)));
+    a.asm_flags.push_back(take(pl.send.size() * sizeof(uint32_t)));
+  }
+  a.coarse = take(2 * (size_t)h.n_coarse * sizeof(double));
+  a.coarse_flags = take((size_t)h.nparts * sizeof(uint32_t));
+  a.red = take(2 * (size_t)h.nparts * RED_W * sizeof(double));
+  a.red_flags = take((size_t)h.nparts * sizeof(uint32_t));
+  a.total = off;
+  return a;
+}
+
+struct LevelDev {
+  int64_t n_own = 0, n_ghost = 0;
+  DevCsr blk[6];
+  DBuf<double> w;     // smoother weight: w/a_ii (Jacobi), 1/l1-diag (l1), 1/(theta a_ii) (Chebyshev zero-guess step)
+  DBuf<double> dinv;  // 1/a_ii (Chebyshev)
+  DBuf<double> x, x2, b, t, d, d2;
+  DBuf<int32_t> send_idx;
+  DBuf<SendNbr> send_nbrs;
+  int n_send = 0, n_send_nbrs = 0, n_recv_nbrs = 0;
+  HaloRecv hr{};
+  // assemble! plan
+  DBuf<AsmSendNbr> asm_nbrs;
+  DBuf<int32_t> asm_rows, asm_ptr, asm_src;
+  int asm_nrows = 0;
+  const double* asm_stage = nullptr;
+  const uint32_t* asm_flags = nullptr;
+  double* xstart = nullptr;  // buffer the zero-guess first sweep is written to (so the V-cycle ends in x)
+};
+
+struct Status {  // host mirror of what we read back
+  DevState st;
+};
+
+}  // namespace
+
+struct PartDev {
+  int part = -1, device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<std::unique_ptr<LevelDev>> lev;
+  ArenaLayout lay;
+  char* arena = nullptr;
+  DBuf<DevState> st;
+  DBuf<double> partials;
+  DBuf<RedPub> red_pubs;
+  RedCtx rc{};
+  DBuf<CoarsePub> coarse_pubs;
+  DBuf<double> inv;
+  DBuf<int64_t> own_gid_L, ghost_gid_L;
+  DBuf<double> xsol, p, q, bsave, hist, scratch4;
+  DBuf<double> io_local;  // own+ghost staging for consistent!/assemble!
+  int hist_cap = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct Engine::Impl {
+  Hierarchy* h = nullptr;
+  int nparts = 0, L = 0;
+  std::vector<std::unique_ptr<PartDev>> parts;         // local parts
+  std::vector<int> local_index;                        // part -> index in parts or -1
+  std::vector<char*> arena_of;                         // part -> arena base as seen from this process
+  std::vector<cudaIpcMemHandle_t> ipc;                 // part -> handle (remote parts)
+  std::vector<char> have_ipc;
+  std::vector<void*> ipc_opened;
+  std::map<int, cudaStream_t> stream_of_device;
+  bool connected = false;
+  int64_t launches = 0;
+  bool counting = true;
+  // exchange needed per level/operator (decided on global metadata so every part agrees)
+  std::vector<char> need_halo_A, need_halo_R, need_halo_P;
+  // graphs (one per distinct stream)
+  std::vector<cudaGraphExec_t> g_iter, g_vcycle;
+  std::vector<cudaStream_t> g_streams;
+  int64_t g_iter_nodes = 0, g_vcycle_nodes = 0;
+  bool g_iter_precond = true;
+  double* flush_buf = nullptr;
+  size_t flush_n = 0;
+  pamg_stats stats{};
+  DevState* pinned = nullptr;  // ring of status snapshots
+  static constexpr int RING = 8;
+  cudaEvent_t ring_ev[RING]{};
+  bool rhs_loaded = false;
+
+  ~Impl();
+  PartDev& P(int i) { return *parts[i]; }
+  void set_dev(const PartDev& p) { CK(cudaSetDevice(p.device)); }
+  // fine-grained blocks (hardware schedules them dynamically, no tail); capped at MAX_GRID because
+  // kernels with a fused reduction write one partial per block
+  static constexpr int MAX_GRID = 16384;
+  int grid_for(int64_t work_items, int items_per_block) const {
+    int64_t g = (work_items + items_per_block - 1) / items_per_block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, MAX_GRID));
+  }
+  void note_launch() {
+    if (counting) ++launches;
+  }
+};
+
+Engine::Impl::~Impl() {
+  for (auto g : g_iter) cudaGraphExecDestroy(g);
+  for (auto g : g_vcycle) cudaGraphExecDestroy(g);
+  for (int k = 0; k < RING; ++k)
+    if (ring_ev[k]) cudaEventDestroy(ring_ev[k]);
+  if (pinned) cudaFreeHost(pinned);
+  for (auto& up : parts) {
+    cudaSetDevice(up->device);
+    if (up->ev0) cudaEventDestroy(up->ev0);
+    if (up->ev1) cudaEventDestroy(up->ev1);
+    if (up->arena) cudaFree(up->arena);
+  }
+  if (flush_buf) cudaFree(flush_buf);
+  for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+  parts.clear();
+  for (auto& kv : stream_of_device) {
+    cudaSetDevice(kv.first);
+    cudaStreamDestroy(kv.second);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <int MODE, bool DOT, bool OG>
+void launch_spmv_lanes(int lanes, int grid, cudaStream_t s, CsrView A, const double* x, const EpiArgs& a, DevState* st,
+                       const HaloRecv& hr, int level, int fixed_parity, double* partials, const RedCtx& rc, int publish,
+                       int slot) {
+#define PAMG_L(LN)                                                                                                  \
+  case LN:                                                                                                          \
+    k_spmv<LN, MODE, DOT, OG><<<grid, BLOCK, 0, s>>>(A, x, a, st, hr, level, fixed_parity, partials, rc, publish, slot); \
+    break;
+  switch (lanes) {
+    PAMG_L(1)
+    PAMG_L(2)
+    PAMG_L(4)
+    PAMG_L(8)
+    PAMG_L(16)
+    PAMG_L(32)
+    default:
+      throw std::runtime_error("bad lanes_per_row");
+  }
+#undef PAMG_L
+}
+
+template <bool DOT, bool OG>
+void launch_spmv_mode(int mode, int lanes, int grid, cudaStream_t s, CsrView A, const double* x, const EpiArgs& a,
+                      DevState* st, const HaloRecv& hr, int level, int fixed_parity, double* partials, const RedCtx& rc,
+                      int publish, int slot) {
+#define PAMG_M(MD)                                                                                           \
+  case MD:                                                                                                   \
+    launch_spmv_lanes<MD, DOT, OG>(lanes, grid, s, A, x, a, st, hr, level, fixed_parity, partials, rc, publish, slot); \
+    break;
+  if (DOT) {
+    switch (mode) {
+      PAMG_M(M_MUL)
+      PAMG_M(M_JACOBI)
+      default:
+        throw std::runtime_error("fused dot only on MUL/JACOBI");
+    }
+  } else {
+    switch (mode) {
+      PAMG_M(M_MUL)
+      PAMG_M(M_RESID)
+      PAMG_M(M_JACOBI)
+      PAMG_M(M_ADD)
+      PAMG_M(M_RESTRICT)
+      PAMG_M(M_CHEB)
+      default:
+        throw std::runtime_error("bad mode");
+    }
+  }
+#undef PAMG_M
+}
+
+}  // namespace
+
+// One SpMV-family operation over all local parts:  [pack halo of xin] ; main (own-own) ; [own-ghost correction].
+// which: PAMG_A_OO / PAMG_P_OO / PAMG_R_OO (the matching *_OG is implied).
+// row_level: level whose LevelDev holds the blocks; halo_level: level of the column partition.
+struct OpSpec {
+  int row_level, which, halo_level, mode;
+  bool dot = false;
+  int slot = 0;
+  bool coarse_ghosts_local = false;  // P at the coarsest level: ghost values were computed locally (parity 0)
+};
+
+void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin, const std::vector<EpiArgs>& epi) {
+  Impl& I = *impl;
+  const int l = op.row_level;
+  bool need;
+  if (op.which == PAMG_A_OO)
+    need = I.need_halo_A[op.halo_level];
+  else if (op.which == PAMG_R_OO)
+    need = I.need_halo_R[l];
+  else
+    need = I.need_halo_P[l];
+  const bool exchange = need && !op.coarse_ghosts_local;
+  // phase 1: producers (never wait)
+  if (exchange)
+    for (size_t i = 0; i < I.parts.size(); ++i) {
+      PartDev& pd = I.P(i);
+      LevelDev& hl = *pd.lev[op.halo_level];
+      if (hl.n_send_nbrs == 0 && hl.n_recv_nbrs == 0) continue;
+      I.set_dev(pd);
+      k_halo_pack<<<I.grid_for(hl.n_send, BLOCK * 4), BLOCK, 0, pd.stream>>>(xin[i], hl.send_idx.p, hl.n_send, hl.send_nbrs.p,
+                                                                             hl.n_send_nbrs, pd.st.p, op.halo_level);
+      I.note_launch();
+    }
+  // phase 2: own-own
+  for (size_t i = 0; i < I.parts.size(); ++i) {
+    PartDev& pd = I.P(i);
+    LevelDev& ld = *pd.lev[l];
+    LevelDev& hl = *pd.lev[op.halo_level];
+    const DevCsr& m = ld.blk[op.which];
+    const bool og_follows = need && hl.n_recv_nbrs > 0;
+    I.set_dev(pd);
+    const int rpb = BLOCK / m.lanes;
+    const int grid = I.grid_for(m.nrows, rpb * 4);
+    if (op.dot)
+      launch_spmv_mode<true, false>(op.mode, m.lanes, grid, pd.stream, m.view(), xin[i], epi[i], pd.st.p, hl.hr, op.halo_level,
+                                    -1, pd.partials.p, pd.rc, og_follows ? 0 : 1, op.slot);
+    else
+      launch_spmv_mode<false, false>(op.mode, m.lanes, grid, pd.stream, m.view(), xin[i], epi[i], pd.st.p, hl.hr,
+                                     op.halo_level, -1, pd.partials.p, pd.rc, 0, 0);
+    I.note_launch();
+  }
+  // phase 3: own-ghost correction (consumers: wait for the neighbours' flags)
+  if (need)
+    for (size_t i = 0; i < I.parts.size(); ++i) {
+      PartDev& pd = I.P(i);
+      LevelDev& ld = *pd.lev[l];
+      LevelDev& hl = *pd.lev[op.halo_level];
+      if (hl.n_recv_nbrs == 0) continue;
+      const DevCsr& m = ld.blk[op.which + 1];
+      I.set_dev(pd);
+      const int rpb = BLOCK / m.lanes;
+      const int grid = I.grid_for(std::max(m.nrows, 1), rpb);
+      const int fixed = op.coarse_ghosts_local ? 0 : -1;
+      if (op.dot)
+        launch_spmv_mode<true, true>(op.mode, m.lanes, grid, pd.stream, m.view(), nullptr, epi[i], pd.st.p, hl.hr,
+                                     op.halo_level, fixed, pd.partials.p, pd.rc, 1, op.slot);
+      else
+        launch_spmv_mode<false, true>(op.mode, m.lanes, grid, pd.stream, m.view(), nullptr, epi[i], pd.st.p, hl.hr,
+                                      op.halo_level, fixed, pd.partials.p, pd.rc, 0, 0);
+      I.note_launch();
+    }
+  CK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------------------------
+Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32_t* device_ids) : impl(new Impl) {
+  Impl& I = *impl;
+  I.h = h;
+  I.nparts = h->nparts;
+  I.L = (int)h->levels.size();
+  if (I.L > MAX_LEVELS) throw std::runtime_error("too many levels");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) throw NoGpuError("no CUDA device available (there is no CPU fallback)");
+  I.local_index.assign(I.nparts, -1);
+  I.arena_of.assign(I.nparts, nullptr);
+  I.ipc.resize(I.nparts);
+  I.have_ipc.assign(I.nparts, 0);
+  const pamg_options& o = h->opts;
+
+  // global decisions (identical in every process because the metadata is replicated)
+  I.need_halo_A.assign(I.L, 0);
+  I.need_halo_R.assign(I.L, 0);
+  I.need_halo_P.assign(I.L, 0);
+  for (int l = 0; l < I.L; ++l)
+    for (int p = 0; p < I.nparts; ++p) {
+      const PartLevel& pl = h->levels[l].parts[p];
+      if (pl.blk[PAMG_A_OG].nnz() > 0) I.need_halo_A[l] = 1;
+      if (pl.blk[PAMG_R_OG].nnz() > 0) I.need_halo_R[l] = 1;
+      if (pl.blk[PAMG_P_OG].nnz() > 0) I.need_halo_P[l] = 1;
+    }
+
+  for (int i = 0; i < nlocal; ++i) {
+    const int part = local_parts[i];
+    if (part < 0 || part >= I.nparts || I.local_index[part] >= 0) throw std::runtime_error("bad local part list");
+    const int dev = device_ids ? device_ids[i] : 0;
+    if (dev < 0 || dev >= ndev) throw std::runtime_error("bad device id");
+    I.local_index[part] = (int)I.parts.size();
+    I.parts.emplace_back(new PartDev);
+    PartDev& pd = *I.parts.back();
+    pd.part = part;
+    pd.device = dev;
+    CK(cudaSetDevice(dev));
+    if (!I.stream_of_device.count(dev)) {
+      cudaStream_t s;
+      CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      I.stream_of_device[dev] = s;
+    }
+    pd.stream = I.stream_of_device[dev];
+    CK(cudaEventCreate(&pd.ev0));
+    CK(cudaEventCreate(&pd.ev1));
+    pd.lay = arena_layout(*h, part);
+    CK(cudaMalloc(&pd.arena, pd.lay.total));
+    CK(cudaMemset(pd.arena, 0, pd.lay.total));
+    I.arena_of[part] = pd.arena;
+    pd.st.alloc(1);
+    pd.partials.alloc(Impl::MAX_GRID + 64);
+    pd.scratch4.alloc(RED_W);
+
+    for (int l = 0; l < I.L; ++l) {
+      const PartLevel& pl = h->levels[l].parts[part];
+      pd.lev.emplace_back(new LevelDev);
+      LevelDev& ld = *pd.lev.back();
+      ld.n_own = pl.n_own;
+      ld.n_ghost = pl.n_ghost;
+      for (int b = 0; b < 6; ++b) {
+        const bool og = (b & 1);
+        int lanes = 0;
+        if (!og && b == PAMG_A_OO && o.lanes_per_row > 0) lanes = o.lanes_per_row;
+        build_csr(pl.blk[b], og, ld.blk[b], og ? 4 : lanes);
+      }
+      // smoother weights
+      std::vector<double> w(pl.n_own), dinv(pl.n_own);
+      const double rho = h->levels[l].rho;
+      const double lmax = o.cheb_hi_frac * rho, lmin = o.cheb_lo_frac * rho;
+      const double theta = 0.5 * (lmax + lmin);
+      for (int64_t k = 0; k < pl.n_own; ++k) {
+        dinv[k] = 1.0 / pl.diag[k];
+        if (o.smoother == PAMG_SMOOTHER_L1JACOBI)
+          w[k] = 1.0 / pl.diag_l1[k];
+        else if (o.smoother == PAMG_SMOOTHER_CHEBYSHEV)
+          w[k] = (1.0 / theta) / pl.diag[k];
+        else
+          w[k] = o.omega_jacobi / pl.diag[k];
+      }
+      ld.w.upload(w);
+      ld.dinv.upload(dinv);
+      ld.x.alloc(pl.n_own);
+      ld.x2.alloc(pl.n_own);
+      ld.b.alloc(pl.n_own);
+      ld.t.alloc(pl.n_own);
+      if (o.smoother == PAMG_SMOOTHER_CHEBYSHEV) {
+        ld.d.alloc(pl.n_own);
+        ld.d2.alloc(pl.n_own);
+      }
+      ld.send_idx.upload(pl.send_idx);
+      ld.n_send = (int)pl.send_idx.size();
+      ld.n_send_nbrs = (int)pl.send.size();
+      ld.n_recv_nbrs = (int)pl.recv.size();
+      ld.hr.ghost[0] = (const double*)(pd.arena + pd.lay.ghost[l]);
+      ld.hr.ghost[1] = ld.hr.ghost[0] + pl.n_ghost;
+      ld.hr.flags = (const uint32_t*)(pd.arena + pd.lay.flags[l]);
+      ld.hr.n_nbrs = ld.n_recv_nbrs;
+      // assemble! gather plan: for every own row that some neighbour holds as a ghost, the staging
+      // positions that contribute to it (ascending neighbour part, ascending slot)
+      {
+        std::vector<std::vector<int32_t>> contrib(pl.n_own);
+        for (size_t k = 0; k < pl.send_idx.size(); ++k) contrib[pl.send_idx[k]].push_back((int32_t)k);
+        std::vector<int32_t> rows, ptr{0}, src;
+        for (int64_t r = 0; r < pl.n_own; ++r)
+          if (!contrib[r].empty()) {
+            rows.push_back((int32_t)r);
+            for (int32_t s : contrib[r]) src.push_back(s);
+            ptr.push_back((int32_t)src.size());
+          }
+        ld.asm_nrows = (int)rows.size();
+        ld.asm_rows.upload(rows);
+        ld.asm_ptr.upload(ptr);
+        ld.asm_src.upload(src);
+        ld.asm_stage = (const double*)(pd.arena + pd.lay.asm_stage[l]);
+        ld.asm_flags = (const uint32_t*)(pd.arena + pd.lay.asm_flags[l]);
+      }
+    }
+    // coarsest solve data
+    const PartLevel& pc = h->levels[I.L - 1].parts[part];
+    pd.inv.upload(h->coarse_inv);
+    pd.own_gid_L.upload(pc.own_to_global);
+    pd.ghost_gid_L.upload(pc.ghost_to_global);
+    // PCG vectors on level 0
+    const int64_t n0 = h->levels[0].parts[part].n_own;
+    pd.xsol.alloc(n0);
+    pd.p.alloc(n0);
+    pd.q.alloc(n0);
+    pd.bsave.alloc(n0);
+    int64_t maxloc = 0;
+    for (int l = 0; l < I.L; ++l) maxloc = std::max(maxloc, h->levels[l].parts[part].n_own + h->levels[l].parts[part].n_ghost);
+    pd.io_local.alloc(maxloc);
+  }
+  CK(cudaMallocHost(&I.pinned, sizeof(DevState) * Impl::RING));
+  for (int k = 0; k < Impl::RING; ++k) CK(cudaEventCreateWithFlags(&I.ring_ev[k], cudaEventDisableTiming));
+  plan_buffers();
+  if (nlocal == I.nparts) connect();
+}
+
+Engine::~Engine() { delete impl; }
+
+// decide, per level, which buffer receives the zero-guess first sweep so that the V-cycle result
+// always ends in LevelDev::x whatever nu_pre / nu_post / Chebyshev degree are
+void Engine::plan_buffers() {
+  Impl& I = *impl;
+  const pamg_options& o = I.h->opts;
+  const int steps = (o.smoother == PAMG_SMOOTHER_CHEBYSHEV) ? std::max(1, o.cheb_degree) : 1;
+  int flips = 1;  // prolongation writes out of place
+  if (o.nu_pre > 0) flips += o.nu_pre * steps - 1;  // the zero-guess first step is written by the producer of b
+  flips += o.nu_post * steps;
+  for (auto& up : I.parts)
+    for (auto& ld : up->lev) ld->xstart = (flips % 2 == 0) ? ld->x.p : ld->x2.p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer wiring
+// ---------------------------------------------------------------------------------------------
+int32_t Engine::handle_bytes() { return (int32_t)sizeof(cudaIpcMemHandle_t); }
+
+void Engine::export_handle(int part, void* blob) {
+  Impl& I = *impl;
+  if (part < 0 || part >= I.nparts || I.local_index[part] < 0) throw std::runtime_error("export: part is not local");
+  PartDev& pd = I.P(I.local_index[part]);
+  I.set_dev(pd);
+  cudaIpcMemHandle_t hdl;
+  CK(cudaIpcGetMemHandle(&hdl, pd.arena));
+  std::memcpy(blob, &hdl, sizeof(hdl));
+}
+
+void Engine::import_handle(int part, const void* blob) {
+  Impl& I = *impl;
+  if (part < 0 || part >= I.nparts) throw std::runtime_error("import: bad part");
+  if (I.local_index[part] >= 0) return;  // local parts need no handle
+  std::memcpy(&I.ipc[part], blob, sizeof(cudaIpcMemHandle_t));
+  I.have_ipc[part] = 1;
+}
+
+void Engine::connect() {
+  Impl& I = *impl;
+  if (I.connected) return;
+  const Hierarchy& h = *I.h;
+  if (I.parts.empty()) throw std::runtime_error("connect: no local parts");
+  // same-process parts on different devices: enable peer access both ways
+  for (auto& a : I.parts)
+    for (auto& b : I.parts)
+      if (a->device != b->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, a->device, b->device));
+        if (!can) throw CommError("devices cannot access each other's memory (P2P required)");
+        CK(cudaSetDevice(a->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+      }
+  // remote parts: map their arenas (one process per GPU => one local device)
+  for (int p = 0; p < I.nparts; ++p) {
+    if (I.local_index[p] >= 0) continue;
+    if (!I.have_ipc[p]) throw CommError("connect: missing handle for remote part " + std::to_string(p));
+    I.set_dev(I.P(0));
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, I.ipc[p], cudaIpcMemLazyEnablePeerAccess));
+    I.ipc_opened.push_back(ptr);
+    I.arena_of[p] = (char*)ptr;
+  }
+  std::vector<ArenaLayout> lay(I.nparts);
+  for (int p = 0; p < I.nparts; ++p) lay[p] = arena_layout(h, p);
+
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    const int me = pd.part;
+    for (int l = 0; l < I.L; ++l) {
+      const PartLevel& pl = h.levels[l].parts[me];
+      LevelDev& ld = *pd.lev[l];
+      std::vector<SendNbr> sn;
+      std::vector<AsmSendNbr> an;
+      for (const Neighbor& nb : pl.send) {
+        const PartLevel& ql = h.levels[l].parts[nb.part];
+        int idx = -1;
+        for (size_t k = 0; k < ql.recv.size(); ++k)
+          if (ql.recv[k].part == me) idx = (int)k;
+        if (idx < 0) throw std::runtime_error("halo plan asymmetry");
+        char* qa = I.arena_of[nb.part];
+        SendNbr s;
+        double* g0 = (double*)(qa + lay[nb.part].ghost[l]);
+        s.ghost[0] = g0 + nb.slot0;
+        s.ghost[1] = g0 + ql.n_ghost + nb.slot0;
+        s.flag = (uint32_t*)(qa + lay[nb.part].flags[l]) + idx;
+        s.offset = (int32_t)nb.offset;
+        s.count = nb.count;
+        sn.push_back(s);
+      }
+      ld.send_nbrs.upload(sn);
+      // assemble!: my ghosts owned by q go to q's staging at the offset of q's send segment for me
+      for (const Neighbor& rb : pl.recv) {
+        const PartLevel& ql = h.levels[l].parts[rb.part];
+        int idx = -1;
+        for (size_t k = 0; k < ql.send.size(); ++k)
+          if (ql.send[k].part == me) idx = (int)k;
+        if (idx < 0) throw std::runtime_error("halo plan asymmetry");
+        char* qa = I.arena_of[rb.part];
+        AsmSendNbr a;
+        a.stage = (double*)(qa + lay[rb.part].asm_stage[l]) + ql.send[idx].offset;
+        a.flag = (uint32_t*)(qa + lay[rb.part].asm_flags[l]) + idx;
+        a.slot0 = rb.slot0;
+        a.count = rb.count;
+        an.push_back(a);
+      }
+      ld.asm_nbrs.upload(an);
+    }
+    std::vector<RedPub> rp(I.nparts);
+    std::vector<CoarsePub> cp(I.nparts);
+    for (int d = 0; d < I.nparts; ++d) {
+      char* qa = I.arena_of[d];
+      double* r0 = (double*)(qa + lay[d].red);
+      rp[d].slot[0] = r0 + (size_t)me * RED_W;
+      rp[d].slot[1] = r0 + (size_t)I.nparts * RED_W + (size_t)me * RED_W;
+      rp[d].flag = (uint32_t*)(qa + lay[d].red_flags) + me;
+      double* c0 = (double*)(qa + lay[d].coarse);
+      cp[d].buf[0] = c0;
+      cp[d].buf[1] = c0 + h.n_coarse;
+      cp[d].flag = (uint32_t*)(qa + lay[d].coarse_flags) + me;
+    }
+    pd.red_pubs.upload(rp);
+    pd.coarse_pubs.upload(cp);
+    pd.rc.pubs = pd.red_pubs.p;
+    pd.rc.local = (const double*)(pd.arena + pd.lay.red);
+    pd.rc.flags = (const uint32_t*)(pd.arena + pd.lay.red_flags);
+    pd.rc.nparts = I.nparts;
+  }
+  I.connected = true;
+}
+
+void Engine::require_connected() {
+  if (!impl->connected) throw CommError("remote parts are not connected: call pamg_comm_import for every remote part, then pamg_comm_connect");
+}
+
+// ---------------------------------------------------------------------------------------------
+// host <-> device vector helpers
+// ---------------------------------------------------------------------------------------------
+void Engine::sync_all() {
+  Impl& I = *impl;
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaStreamSynchronize(up->stream));
+  }
+}
+
+void Engine::upload_vec(int level, const double* const* host, int which_buf) {
+  Impl& I = *impl;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    if (!host[pd.part]) throw std::runtime_error("null vector pointer for a local part");
+    CK(cudaMemcpyAsync(vec(pd, level, which_buf), host[pd.part], pd.lev[level]->n_own * sizeof(double), cudaMemcpyHostToDevice,
+                       pd.stream));
+  }
+}
+
+void Engine::download_vec(int level, double* const* host, int which_buf) {
+  Impl& I = *impl;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    if (!host[pd.part]) throw std::runtime_error("null vector pointer for a local part");
+    CK(cudaMemcpyAsync(host[pd.part], vec(pd, level, which_buf), pd.lev[level]->n_own * sizeof(double), cudaMemcpyDeviceToHost,
+                       pd.stream));
+  }
+  sync_all();
+}
+
+double* Engine::vec(PartDev& pd, int level, int which) {
+  LevelDev& ld = *pd.lev[level];
+  switch (which) {
+    case V_X: return ld.x.p;
+    case V_X2: return ld.x2.p;
+    case V_B: return ld.b.p;
+    case V_T: return ld.t.p;
+    case V_XSTART: return ld.xstart;
+    case V_XSOL: return pd.xsol.p;
+    case V_P: return pd.p.p;
+    case V_Q: return pd.q.p;
+    case V_BSAVE: return pd.bsave.p;
+    default: throw std::runtime_error("bad vector id");
+  }
+}
+
+void Engine::check_device_error() {
+  Impl& I = *impl;
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    DevState s;
+    CK(cudaMemcpy(&s, up->st.p, sizeof(s), cudaMemcpyDeviceToHost));
+    if (s.error) {
+      CK(cudaMemset(&up->st.p->error, 0, sizeof(int32_t)));
+      throw CommError("halo/all-reduce wait timed out on part " + std::to_string(up->part));
+    }
+  }
+}
+
+void Engine::clear_done() {
+  Impl& I = *impl;
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaMemsetAsync(&up->st.p->done, 0, sizeof(int32_t), up->stream));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// level operations (enqueue only)
+// ---------------------------------------------------------------------------------------------
+std::vector<const double*> Engine::ptrs(int level, int which) {
+  std::vector<const double*> v;
+  for (auto& up : impl->parts) v.push_back(vec(*up, level, which));
+  return v;
+}
+
+// one smoother "sweep" from `cur` into the other ping-pong buffer(s); returns the new current id.
+// dot_r: fuse sum(dotv .* result) on the LAST step (level-0 post-smoothing, r.z for PCG).
+void Engine::enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_guess_done, bool dot_last) {
+  Impl& I = *impl;
+  const pamg_options& o = I.h->opts;
+  const size_t np = I.parts.size();
+  auto other = [&](size_t i) {
+    LevelDev& ld = *I.P(i).lev[l];
+    return cur[i] == ld.x.p ? ld.x2.p : ld.x.p;
+  };
+  if (o.smoother != PAMG_SMOOTHER_CHEBYSHEV) {
+    for (int s = zero_guess_done ? 1 : 0; s < nu; ++s) {
+      std::vector<EpiArgs> epi(np);
+      std::vector<const double*> xin(np);
+      std::vector<double*> nxt(np);
+      const bool dot = dot_last && s == nu - 1;
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& ld = *I.P(i).lev[l];
+        nxt[i] = other(i);
+        xin[i] = cur[i];
+        epi[i] = EpiArgs{nxt[i], ld.b.p, cur[i], ld.w.p, nullptr, nullptr, dot ? ld.b.p : nullptr, 0.0, 0.0};
+      }
+      OpSpec op{l, PAMG_A_OO, l, M_JACOBI, dot, 1, false};
+      enqueue_op(op, xin, epi);
+      cur = nxt;
+    }
+    return;
+  }
+  // Chebyshev (three-term recurrence; oracle/amg_oracle.py chebyshev())
+  const double rho = I.h->levels[l].rho;
+  const double lmax = o.cheb_hi_frac * rho, lmin = o.cheb_lo_frac * rho;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  const int deg = std::max(1, o.cheb_degree);
+  for (int s = 0; s < nu; ++s) {
+    double rho_k = 1.0 / sigma;
+    std::vector<const double*> dcur(np, nullptr);  // d of the previous step
+    for (int k = 0; k < deg; ++k) {
+      const bool skip = (s == 0 && k == 0 && zero_guess_done);  // x = d = (1/theta) D^-1 b already in cur
+      double c1 = 0.0, c2 = 1.0 / theta;
+      if (k > 0) {
+        const double rho_n = 1.0 / (2.0 * sigma - rho_k);
+        c1 = rho_n * rho_k;
+        c2 = 2.0 * rho_n / delta;
+        rho_k = rho_n;
+      }
+      if (skip) {
+        for (size_t i = 0; i < np; ++i) dcur[i] = cur[i];
+        continue;
+      }
+      std::vector<EpiArgs> epi(np);
+      std::vector<const double*> xin(np);
+      std::vector<double*> nxt(np);
+      const bool dot = dot_last && s == nu - 1 && k == deg - 1;
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& ld = *I.P(i).lev[l];
+        nxt[i] = other(i);
+        xin[i] = cur[i];
+        double* dnew = (dcur[i] == ld.d.p) ? ld.d2.p : ld.d.p;
+        epi[i] = EpiArgs{nxt[i], ld.b.p, cur[i], ld.dinv.p, dnew, k > 0 ? dcur[i] : nullptr, dot ? ld.b.p : nullptr, c1, c2};
+        dcur[i] = dnew;
+      }
+      if (dot) throw std::runtime_error("internal: fused dot is not instantiated for Chebyshev");
+      OpSpec op{l, PAMG_A_OO, l, M_CHEB, false, 0, false};
+      enqueue_op(op, xin, epi);
+      cur = nxt;
+    }
+  }
+}
+
+void Engine::enqueue_coarse_solve() {
+  Impl& I = *impl;
+  const int l = I.L - 1;
+  const int n = (int)I.h->n_coarse;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[l];
+    I.set_dev(pd);
+    k_coarse_gather<<<I.grid_for(ld.n_own, BLOCK), BLOCK, 0, pd.stream>>>(ld.b.p, pd.own_gid_L.p, (int)ld.n_own, pd.coarse_pubs.p,
+                                                                         I.nparts, pd.st.p);
+    I.note_launch();
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[l];
+    I.set_dev(pd);
+    const int rows = (int)(ld.n_own + ld.n_ghost);
+    const double* c0 = (const double*)(pd.arena + pd.lay.coarse);
+    k_coarse_solve<<<I.grid_for(std::max(rows, 1), BLOCK / 32), BLOCK, 0, pd.stream>>>(
+        pd.inv.p, n, c0, c0 + n, (const uint32_t*)(pd.arena + pd.lay.coarse_flags), I.nparts, pd.own_gid_L.p, (int)ld.n_own,
+        pd.ghost_gid_L.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
+    I.note_launch();
+  }
+  CK(cudaGetLastError());
+}
+
+// V-cycle from level l.  Preconditions: lev[l].b holds the right-hand side and lev[l].xstart holds
+// the zero-guess first pre-smoothing step (w .* b, or 0 when nu_pre == 0).  Result in lev[l].x.
+void Engine::enqueue_vcycle(int l, bool dot_rz) {
+  Impl& I = *impl;
+  const pamg_options& o = I.h->opts;
+  const size_t np = I.parts.size();
+  if (l == I.L - 1) {
+    enqueue_coarse_solve();
+    return;
+  }
+  std::vector<double*> cur(np);
+  for (size_t i = 0; i < np; ++i) cur[i] = I.P(i).lev[l]->xstart;
+  if (o.nu_pre > 0) enqueue_smooth(l, o.nu_pre, cur, /*zero_guess_done=*/true, false);
+  // residual t = b - A x
+  {
+    std::vector<EpiArgs> epi(np);
+    std::vector<const double*> xin(np);
+    for (size_t i = 0; i < np; ++i) {
+      LevelDev& ld = *I.P(i).lev[l];
+      xin[i] = cur[i];
+      epi[i] = EpiArgs{ld.t.p, ld.b.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+    }
+    OpSpec op{l, PAMG_A_OO, l, M_RESID, false, 0, false};
+    enqueue_op(op, xin, epi);
+  }
+  // restriction b_c = R t, fused with the coarse level's zero-guess first smoothing step
+  {
+    const bool coarse_is_last = (l + 1 == I.L - 1);
+    std::vector<EpiArgs> epi(np);
+    std::vector<const double*> xin(np);
+    for (size_t i = 0; i < np; ++i) {
+      LevelDev& ld = *I.P(i).lev[l];
+      LevelDev& lc = *I.P(i).lev[l + 1];
+      xin[i] = ld.t.p;
+      double* out2 = coarse_is_last ? nullptr : lc.xstart;
+      const double* w = (o.nu_pre > 0) ? lc.w.p : nullptr;
+      epi[i] = EpiArgs{lc.b.p, nullptr, nullptr, w, out2, nullptr, nullptr, 0.0, 0.0};
+      if (out2 && !w) epi[i].out2 = nullptr;  // nu_pre == 0: xstart is zeroed below instead
+    }
+    OpSpec op{l, PAMG_R_OO, l, M_RESTRICT, false, 0, false};
+    enqueue_op(op, xin, epi);
+    if (!coarse_is_last && o.nu_pre == 0)
+      for (size_t i = 0; i < np; ++i) {
+        PartDev& pd = I.P(i);
+        LevelDev& lc = *pd.lev[l + 1];
+        I.set_dev(pd);
+        k_scale<<<I.grid_for(lc.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(lc.b.p, nullptr, lc.xstart, (int)lc.n_own, pd.st.p);
+        I.note_launch();
+      }
+  }
+  enqueue_vcycle(l + 1, false);
+  // prolongation + correction (out of place): nxt = cur + P e_c
+  {
+    std::vector<EpiArgs> epi(np);
+    std::vector<const double*> xin(np);
+    std::vector<double*> nxt(np);
+    for (size_t i = 0; i < np; ++i) {
+      LevelDev& ld = *I.P(i).lev[l];
+      LevelDev& lc = *I.P(i).lev[l + 1];
+      nxt[i] = (cur[i] == ld.x.p) ? ld.x2.p : ld.x.p;
+      xin[i] = lc.x.p;
+      epi[i] = EpiArgs{nxt[i], cur[i], nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+    }
+    OpSpec op{l, PAMG_P_OO, l + 1, M_ADD, false, 0, (l + 1 == I.L - 1)};
+    enqueue_op(op, xin, epi);
+    cur = nxt;
+  }
+  if (o.nu_post > 0) enqueue_smooth(l, o.nu_post, cur, false, dot_rz);
+  for (size_t i = 0; i < np; ++i)
+    if (cur[i] != I.P(i).lev[l]->x.p) throw std::runtime_error("internal: V-cycle buffer plan mismatch");
+}
+
+// r.z when the V-cycle could not fuse it (nu_post == 0, Chebyshev, or a single-level hierarchy)
+void Engine::enqueue_dot_rz() {
+  Impl& I = *impl;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& l0 = *pd.lev[0];
+    I.set_dev(pd);
+    k_dot<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p, pd.rc,
+                                                                   1, 1);
+    I.note_launch();
+  }
+  CK(cudaGetLastError());
+}
+
+bool Engine::vcycle_fuses_rz() const {
+  const pamg_options& o = impl->h->opts;
+  return impl->L > 1 && o.nu_post > 0 && o.smoother != PAMG_SMOOTHER_CHEBYSHEV;
+}
+
+// one PCG iteration (uniform body, see DESIGN.md "PCG schedule"):
+//   z = M^-1 r (rz fused) ; beta = rz/rho_old ; p = z + beta p ; q = A p (pq fused) ;
+//   alpha = rz/pq ; x += alpha p ; r -= alpha q ; z0 = w .* r ; rr ; check
+void Engine::enqueue_pcg_iteration(bool precond) {
+  Impl& I = *impl;
+  const size_t np = I.parts.size();
+  if (precond) {
+    enqueue_vcycle(0, vcycle_fuses_rz());
+    if (!vcycle_fuses_rz()) enqueue_dot_rz();
+  } else {
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& l0 = *pd.lev[0];
+      I.set_dev(pd);
+      k_copy_dot<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p,
+                                                                          pd.rc);
+      I.note_launch();
+    }
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& l0 = *pd.lev[0];
+    I.set_dev(pd);
+    k_update_p<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.x.p, pd.p.p, (int)l0.n_own, pd.st.p, pd.rc);
+    I.note_launch();
+  }
+  {
+    std::vector<EpiArgs> epi(np);
+    std::vector<const double*> xin(np);
+    for (size_t i = 0; i < np; ++i) {
+      PartDev& pd = I.P(i);
+      xin[i] = pd.p.p;
+      epi[i] = EpiArgs{pd.q.p, nullptr, nullptr, nullptr, nullptr, nullptr, pd.p.p, 0.0, 0.0};
+    }
+    OpSpec op{0, PAMG_A_OO, 0, M_MUL, true, 2, false};
+    enqueue_op(op, xin, epi);
+  }
+  const bool zero_guess = precond && I.L > 1 && I.h->opts.nu_pre > 0;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& l0 = *pd.lev[0];
+    I.set_dev(pd);
+    k_update_xr<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.xsol.p, l0.b.p, pd.p.p, pd.q.p, l0.xstart,
+                                                                         zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
+                                                                         pd.partials.p, pd.rc);
+    I.note_launch();
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p);
+    I.note_launch();
+  }
+  CK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph capture over all local streams
+// ---------------------------------------------------------------------------------------------
+template <class F>
+void Engine::capture(std::vector<cudaGraphExec_t>& out, int64_t* nodes, F&& body) {
+  Impl& I = *impl;
+  for (auto g : out) cudaGraphExecDestroy(g);
+  out.clear();
+  I.g_streams.clear();
+  for (auto& kv : I.stream_of_device) I.g_streams.push_back(kv.second);
+  std::vector<int> devs;
+  for (auto& kv : I.stream_of_device) devs.push_back(kv.first);
+  for (size_t k = 0; k < I.g_streams.size(); ++k) {
+    CK(cudaSetDevice(devs[k]));
+    CK(cudaStreamBeginCapture(I.g_streams[k], cudaStreamCaptureModeRelaxed));
+  }
+  const int64_t before = I.launches;
+  std::string err;
+  try {
+    body();
+  } catch (const std::exception& e) {
+    err = e.what();
+  }
+  *nodes = I.launches - before;
+  I.launches = before;
+  for (size_t k = 0; k < I.g_streams.size(); ++k) {
+    CK(cudaSetDevice(devs[k]));
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(I.g_streams[k], &g);
+    if (e != cudaSuccess && err.empty()) err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e);
+    if (g && err.empty()) {
+      cudaGraphExec_t ge = nullptr;
+      e = cudaGraphInstantiate(&ge, g, 0);
+      if (e != cudaSuccess)
+        err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e);
+      else
+        out.push_back(ge);
+    }
+    if (g) cudaGraphDestroy(g);
+  }
+  if (!err.empty()) throw CudaError("graph capture failed: " + err);
+}
+
+void Engine::launch_graphs(const std::vector<cudaGraphExec_t>& gs, int64_t nodes) {
+  Impl& I = *impl;
+  size_t k = 0;
+  for (auto& kv : I.stream_of_device) {
+    CK(cudaSetDevice(kv.first));
+    CK(cudaGraphLaunch(gs[k], kv.second));
+    ++k;
+  }
+  I.launches += nodes;
+}
+
+// ---------------------------------------------------------------------------------------------
+// public operations
+// ---------------------------------------------------------------------------------------------
+void Engine::spmv(int level, const double* const* x, double* const* y) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L) throw std::runtime_error("bad level");
+  I.launches = 0;
+  clear_done();
+  upload_vec(level, x, V_X);
+  const size_t np = I.parts.size();
+  std::vector<EpiArgs> epi(np);
+  for (size_t i = 0; i < np; ++i)
+    epi[i] = EpiArgs{I.P(i).lev[level]->t.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+  OpSpec op{level, PAMG_A_OO, level, M_MUL, false, 0, false};
+  enqueue_op(op, ptrs(level, V_X), epi);
+  download_vec(level, y, V_T);
+  check_device_error();
+}
+
+void Engine::smooth(int level, int nu, const double* const* b, double* const* x) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L) throw std::runtime_error("bad level");
+  I.launches = 0;
+  clear_done();
+  upload_vec(level, b, V_B);
+  upload_vec(level, x, V_X);
+  std::vector<double*> cur;
+  for (auto& up : I.parts) cur.push_back(up->lev[level]->x.p);
+  enqueue_smooth(level, nu, cur, false, false);
+  for (size_t i = 0; i < I.parts.size(); ++i) {
+    PartDev& pd = I.P(i);
+    I.set_dev(pd);
+    CK(cudaMemcpyAsync(x[pd.part], cur[i], pd.lev[level]->n_own * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
+  }
+  sync_all();
+  check_device_error();
+}
+
+void Engine::residual_restrict(int level, const double* const* b, const double* const* x, double* const* r, double* const* bc) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L - 1) throw std::runtime_error("bad level");
+  I.launches = 0;
+  clear_done();
+  upload_vec(level, b, V_B);
+  upload_vec(level, x, V_X);
+  const size_t np = I.parts.size();
+  std::vector<EpiArgs> epi(np);
+  for (size_t i = 0; i < np; ++i) {
+    LevelDev& ld = *I.P(i).lev[level];
+    epi[i] = EpiArgs{ld.t.p, ld.b.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+  }
+  OpSpec op{level, PAMG_A_OO, level, M_RESID, false, 0, false};
+  enqueue_op(op, ptrs(level, V_X), epi);
+  for (size_t i = 0; i < np; ++i) {
+    LevelDev& lc = *I.P(i).lev[level + 1];
+    epi[i] = EpiArgs{lc.b.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+  }
+  OpSpec op2{level, PAMG_R_OO, level, M_RESTRICT, false, 0, false};
+  enqueue_op(op2, ptrs(level, V_T), epi);
+  if (r) download_vec(level, r, V_T);
+  download_vec(level + 1, bc, V_B);
+  check_device_error();
+}
+
+void Engine::prolong_correct(int level, const double* const* ec, double* const* x) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L - 1) throw std::runtime_error("bad level");
+  I.launches = 0;
+  clear_done();
+  upload_vec(level, x, V_X);
+  upload_vec(level + 1, ec, V_X);
+  const size_t np = I.parts.size();
+  std::vector<EpiArgs> epi(np);
+  for (size_t i = 0; i < np; ++i) {
+    LevelDev& ld = *I.P(i).lev[level];
+    epi[i] = EpiArgs{ld.x2.p, ld.x.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+  }
+  OpSpec op{level, PAMG_P_OO, level + 1, M_ADD, false, 0, false};
+  enqueue_op(op, ptrs(level + 1, V_X), epi);
+  download_vec(level, x, V_X2);
+  check_device_error();
+}
+
+double Engine::dot(int level, const double* const* u, const double* const* v) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L) throw std::runtime_error("bad level");
+  I.launches = 0;
+  upload_vec(level, u, V_X);
+  upload_vec(level, v, V_B);
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[level];
+    I.set_dev(pd);
+    k_dot<<<I.grid_for(ld.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
+    I.note_launch();
+  }
+  double out[RED_W] = {0, 0, 0, 0};
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    k_red_read<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.scratch4.p);
+    I.note_launch();
+  }
+  CK(cudaGetLastError());
+  sync_all();
+  I.set_dev(I.P(0));
+  CK(cudaMemcpy(out, I.P(0).scratch4.p, sizeof(out), cudaMemcpyDeviceToHost));
+  check_device_error();
+  return out[3];
+}
+
+void Engine::consistent(int level, double* const* v) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L) throw std::runtime_error("bad level");
+  I.launches = 0;
+  clear_done();
+  upload_vec(level, v, V_X);
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[level];
+    if (ld.n_send_nbrs == 0 && ld.n_recv_nbrs == 0) continue;
+    I.set_dev(pd);
+    k_halo_pack<<<I.grid_for(ld.n_send, BLOCK * 4), BLOCK, 0, pd.stream>>>(ld.x.p, ld.send_idx.p, ld.n_send, ld.send_nbrs.p,
+                                                                           ld.n_send_nbrs, pd.st.p, level);
+    I.note_launch();
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[level];
+    if (ld.n_recv_nbrs == 0) continue;
+    I.set_dev(pd);
+    k_halo_unpack<<<I.grid_for(ld.n_ghost, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.io_local.p, ld.hr, (int)ld.n_ghost, pd.st.p, level);
+    I.note_launch();
+    CK(cudaMemcpyAsync(v[pd.part] + ld.n_own, pd.io_local.p, ld.n_ghost * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
+  }
+  CK(cudaGetLastError());
+  sync_all();
+  check_device_error();
+}
+
+void Engine::assemble(int level, double* const* v) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L) throw std::runtime_error("bad level");
+  I.launches = 0;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[level];
+    I.set_dev(pd);
+    CK(cudaMemcpyAsync(pd.io_local.p, v[pd.part], (ld.n_own + ld.n_ghost) * sizeof(double), cudaMemcpyHostToDevice, pd.stream));
+    if (ld.n_send_nbrs == 0 && ld.n_recv_nbrs == 0) continue;
+    k_asm_pack<<<I.grid_for(ld.n_ghost, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.io_local.p + ld.n_own, ld.asm_nbrs.p, ld.n_recv_nbrs,
+                                                                           pd.st.p, level);
+    I.note_launch();
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& ld = *pd.lev[level];
+    I.set_dev(pd);
+    if (ld.n_send_nbrs > 0) {
+      k_asm_add<<<I.grid_for(std::max(ld.asm_nrows, 1), BLOCK), BLOCK, 0, pd.stream>>>(
+          pd.io_local.p, ld.asm_rows.p, ld.asm_ptr.p, ld.asm_src.p, ld.asm_nrows, ld.asm_stage, ld.asm_flags, ld.n_send_nbrs,
+          pd.st.p, level);
+      I.note_launch();
+    }
+    CK(cudaMemsetAsync(pd.io_local.p + ld.n_own, 0, ld.n_ghost * sizeof(double), pd.stream));
+    CK(cudaMemcpyAsync(v[pd.part], pd.io_local.p, (ld.n_own + ld.n_ghost) * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
+  }
+  CK(cudaGetLastError());
+  sync_all();
+  check_device_error();
+}
+
+void Engine::enqueue_vcycle_entry() {
+  // b is in lev[0].b; write the zero-guess first step into xstart, then the cycle
+  Impl& I = *impl;
+  const pamg_options& o = I.h->opts;
+  if (I.L > 1)
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& l0 = *pd.lev[0];
+      I.set_dev(pd);
+      k_scale<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.b.p, o.nu_pre > 0 ? l0.w.p : nullptr, l0.xstart,
+                                                                       (int)l0.n_own, pd.st.p);
+      I.note_launch();
+    }
+  enqueue_vcycle(0, false);
+}
+
+void Engine::vcycle(const double* const* b, double* const* x) {
+  require_connected();
+  Impl& I = *impl;
+  I.launches = 0;
+  clear_done();
+  upload_vec(0, b, V_B);
+  const bool use_graph = I.h->opts.use_graph != 0;
+  if (use_graph && I.g_vcycle.empty()) capture(I.g_vcycle, &I.g_vcycle_nodes, [&] { enqueue_vcycle_entry(); });
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventRecord(up->ev0, up->stream));
+  }
+  if (use_graph)
+    launch_graphs(I.g_vcycle, I.g_vcycle_nodes);
+  else
+    enqueue_vcycle_entry();
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventRecord(up->ev1, up->stream));
+  }
+  download_vec(0, x, V_X);
+  float ms = 0, mx = 0;
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventElapsedTime(&ms, up->ev0, up->ev1));
+    mx = std::max(mx, ms);
+  }
+  I.stats.vcycle_ms = mx;
+  I.stats.kernel_launches = I.launches;
+  check_device_error();
+}
+
+void Engine::load_rhs(const double* const* b) {
+  upload_vec(0, b, V_BSAVE);
+  sync_all();
+  impl->rhs_loaded = true;
+}
+
+void Engine::read_solution(double* const* x) { download_vec(0, x, V_XSOL); }
+
+int Engine::pcg(const double* const* b, double* const* x, double rtol, int maxiter, bool precond, int* iters, double* hist) {
+  load_rhs(b);
+  int rc = pcg_resident(rtol, maxiter, precond, iters, hist);
+  read_solution(x);
+  return rc;
+}
+
+int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, double* hist) {
+  require_connected();
+  Impl& I = *impl;
+  if (!I.rhs_loaded) throw std::runtime_error("pamg_pcg_resident: call pamg_load_rhs first");
+  if (maxiter < 0) throw std::runtime_error("maxiter < 0");
+  I.launches = 0;
+  const bool use_graph = I.h->opts.use_graph != 0;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    if (pd.hist_cap < maxiter + 2) {
+      pd.hist.alloc(maxiter + 2);
+      pd.hist_cap = maxiter + 2;
+      for (auto g : I.g_iter) cudaGraphExecDestroy(g);  // hist pointer is baked into the graph
+      I.g_iter.clear();
+    }
+  }
+  if (use_graph && (I.g_iter.empty() || I.g_iter_precond != precond)) {
+    capture(I.g_iter, &I.g_iter_nodes, [&] { enqueue_pcg_iteration(precond); });
+    I.g_iter_precond = precond;
+  }
+  const bool zero_guess = precond && I.L > 1 && I.h->opts.nu_pre > 0;
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& l0 = *pd.lev[0];
+    I.set_dev(pd);
+    CK(cudaEventRecord(pd.ev0, pd.stream));
+    k_pcg_init<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.bsave.p, pd.xsol.p, l0.b.p, pd.p.p, l0.xstart,
+                                                                        zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
+                                                                        pd.partials.p, pd.rc, rtol, maxiter);
+    I.note_launch();
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p);
+    I.note_launch();
+  }
+  CK(cudaGetLastError());
+  // speculative enqueue: iteration k+1 is launched before the status of iteration k is known; every
+  // kernel early-outs once the device-side `done` flag is set, so the extra launch is a no-op.
+  PartDev& p0 = I.P(0);
+  const int LOOKAHEAD = 1;
+  bool finished = false;
+  int launched = 0;
+  while (!finished) {
+    if (launched < maxiter) {
+      if (use_graph)
+        launch_graphs(I.g_iter, I.g_iter_nodes);
+      else
+        enqueue_pcg_iteration(precond);
+    }
+    I.set_dev(p0);
+    const int slot = launched % Impl::RING;
+    CK(cudaMemcpyAsync(&I.pinned[slot], p0.st.p, sizeof(DevState), cudaMemcpyDeviceToHost, p0.stream));
+    CK(cudaEventRecord(I.ring_ev[slot], p0.stream));
+    ++launched;
+    if (launched > LOOKAHEAD) {
+      const int s2 = (launched - 1 - LOOKAHEAD) % Impl::RING;
+      CK(cudaEventSynchronize(I.ring_ev[s2]));
+      if (I.pinned[s2].done || I.pinned[s2].error) finished = true;
+    }
+    if (launched > maxiter + LOOKAHEAD + 1) finished = true;
+  }
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventRecord(up->ev1, up->stream));
+  }
+  sync_all();
+  DevState fin;
+  I.set_dev(p0);
+  CK(cudaMemcpy(&fin, p0.st.p, sizeof(fin), cudaMemcpyDeviceToHost));
+  float ms = 0, mx = 0;
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventElapsedTime(&ms, up->ev0, up->ev1));
+    mx = std::max(mx, ms);
+  }
+  check_device_error();
+  const double r0 = std::sqrt(fin.sc[SC_RR0]), rn = std::sqrt(fin.sc[SC_RR]);
+  const bool conv = rn <= rtol * r0;
+  if (iters) *iters = fin.iters;
+  if (hist && fin.iters >= 0) CK(cudaMemcpy(hist, p0.hist.p, (fin.iters + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  I.stats.iters = fin.iters;
+  I.stats.converged = conv;
+  I.stats.r0_norm = r0;
+  I.stats.r_norm = rn;
+  I.stats.solve_ms = mx;
+  I.stats.kernel_launches = I.launches;
+  return conv ? PAMG_OK : PAMG_ERR_NOTCONV;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel timing hook (bench.py roofline leg)
+// ---------------------------------------------------------------------------------------------
+void Engine::time_kernel(int kind, int level, int reps, bool flush_l2, float* ms_out) {
+  require_connected();
+  Impl& I = *impl;
+  if (level < 0 || level >= I.L) throw std::runtime_error("bad level");
+  if ((kind == 2 || kind == 3) && level >= I.L - 1) throw std::runtime_error("no transfer operator on the coarsest level");
+  PartDev& p0 = I.P(0);
+  I.set_dev(p0);
+  if (flush_l2 && !I.flush_buf) {
+    I.flush_n = (size_t)(256u << 20) / sizeof(double);
+    CK(cudaMalloc(&I.flush_buf, I.flush_n * sizeof(double)));
+    CK(cudaMemset(I.flush_buf, 0, I.flush_n * sizeof(double)));
+  }
+  const size_t np = I.parts.size();
+  clear_done();
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int r = 0; r < reps; ++r) {
+    if (flush_l2) {
+      I.set_dev(p0);
+      k_flush<<<148 * 8, 256, 0, p0.stream>>>(I.flush_buf, I.flush_n);
+    }
+    I.set_dev(p0);
+    CK(cudaEventRecord(e0, p0.stream));
+    std::vector<EpiArgs> epi(np);
+    if (kind == 0) {
+      for (size_t i = 0; i < np; ++i)
+        epi[i] = EpiArgs{I.P(i).lev[level]->t.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+      enqueue_op(OpSpec{level, PAMG_A_OO, level, M_MUL, false, 0, false}, ptrs(level, V_X), epi);
+    } else if (kind == 1) {
+      std::vector<double*> cur;
+      for (auto& up : I.parts) cur.push_back(up->lev[level]->x.p);
+      enqueue_smooth(level, 1, cur, false, false);
+    } else if (kind == 2) {
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& ld = *I.P(i).lev[level];
+        epi[i] = EpiArgs{ld.t.p, ld.b.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+      }
+      enqueue_op(OpSpec{level, PAMG_A_OO, level, M_RESID, false, 0, false}, ptrs(level, V_X), epi);
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& lc = *I.P(i).lev[level + 1];
+        epi[i] = EpiArgs{lc.b.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+      }
+      enqueue_op(OpSpec{level, PAMG_R_OO, level, M_RESTRICT, false, 0, false}, ptrs(level, V_T), epi);
+    } else if (kind == 3) {
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& ld = *I.P(i).lev[level];
+        epi[i] = EpiArgs{ld.x2.p, ld.x.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+      }
+      enqueue_op(OpSpec{level, PAMG_P_OO, level + 1, M_ADD, false, 0, false}, ptrs(level + 1, V_X), epi);
+    } else if (kind == 4) {
+      for (auto& up : I.parts) {
+        PartDev& pd = *up;
+        LevelDev& ld = *pd.lev[level];
+        I.set_dev(pd);
+        k_dot<<<I.grid_for(ld.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
+      }
+    } else if (kind == 5) {
+      const bool use_graph = I.h->opts.use_graph != 0;
+      if (use_graph && I.g_vcycle.empty()) capture(I.g_vcycle, &I.g_vcycle_nodes, [&] { enqueue_vcycle_entry(); });
+      if (use_graph)
+        launch_graphs(I.g_vcycle, I.g_vcycle_nodes);
+      else
+        enqueue_vcycle_entry();
+    } else {
+      throw std::runtime_error("bad kernel kind");
+    }
+    I.set_dev(p0);
+    CK(cudaEventRecord(e1, p0.stream));
+    sync_all();
+    CK(cudaEventElapsedTime(&ms_out[r], e0, e1));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  check_device_error();
+}
+
+void Engine::get_stats(pamg_stats* s) {
+  Impl& I = *impl;
+  *s = I.stats;
+  s->n_levels = I.L;
+  for (int l = 0; l < 16; ++l) {
+    s->format[l] = l < I.L ? PAMG_FORMAT_CSR : 0;
+    s->lanes[l] = (l < I.L && !I.parts.empty()) ? I.P(0).lev[l]->blk[PAMG_A_OO].lanes : 0;
+  }
+}
+
+}  // namespace pamg

@@ -1,0 +1,83 @@
+// host.hpp — host-side data model of the partitioned AMG hierarchy (product code).
+//
+// Mirrors the PartitionedArrays.jl objects the solve phase consumes (SURVEY.md App. A,
+// [RECALL-UNVERIFIED]; the reference snapshot /root/reference/README.md:1-2 has no code):
+//   PRange / index partition  -> PartLevel::{own_to_global, ghost_to_global, ghost_to_owner}
+//   PSparseMatrix split blocks -> LocalCsr A_oo/A_og (+ P, R of the AMG level)
+//   exchange plan of consistent!/assemble! -> PartLevel::{recv, send, send_idx}
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/pamg.h"
+
+namespace pamg {
+
+struct Csr {  // global matrix, global ids, sorted columns
+  int64_t nrows = 0, ncols = 0;
+  std::vector<int64_t> ptr, col;
+  std::vector<double> val;
+  int64_t nnz() const { return (int64_t)col.size(); }
+};
+
+struct LocalCsr {  // one block of the split format; local int32 column ids
+  int64_t nrows = 0, ncols = 0;
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> col;
+  std::vector<double> val;
+  int64_t nnz() const { return (int64_t)col.size(); }
+};
+
+struct Neighbor {
+  int32_t part;    // the other part
+  int32_t slot0;   // recv: first ghost slot here; send: first ghost slot in the peer
+  int32_t count;
+  int64_t offset;  // send: offset into send_idx
+};
+
+struct PartLevel {
+  bool present = false;
+  int64_t n_own = 0, n_ghost = 0, n_own_coarse = 0, n_ghost_coarse = 0;
+  std::vector<int64_t> own_to_global, ghost_to_global;
+  std::vector<int32_t> ghost_to_owner;
+  LocalCsr blk[6];  // PAMG_A_OO .. PAMG_R_OG
+  std::vector<double> diag, diag_l1;
+  std::vector<int32_t> agg_local;
+  std::vector<Neighbor> recv, send;
+  std::vector<int32_t> send_idx;
+};
+
+struct Level {
+  int64_t n_global = 0;
+  double rho = 0.0, omega_p = 0.0;
+  std::vector<PartLevel> parts;
+};
+
+struct Hierarchy {
+  int32_t nparts = 0;
+  pamg_options opts{};
+  std::vector<Level> levels;
+  int64_t n_coarse = 0;
+  std::vector<double> coarse_inv;            // row-major n_coarse x n_coarse
+  std::vector<int64_t> coarse_part_offset;   // nparts+1, own range of each part on the coarsest level
+  bool ready = false;
+};
+
+// ---- gallery / partition (host_setup.cpp) ---------------------------------------------------
+void local_range(int64_t p, int64_t nparts, int64_t n, int64_t* off, int64_t* len);
+void uniform_partition(int ndim, const int64_t* dims, const int32_t* pdims, std::vector<int32_t>& owner);
+void gallery_poisson(int ndim, const int64_t* dims, Csr& A);
+void gallery_diffusion_jump(int ndim, const int64_t* dims, int blocks, double kmax, double eps_z, Csr& A);
+void matvec(const Csr& A, const double* x, double* y);
+
+// ---- setup ------------------------------------------------------------------------------------
+// Builds every level (global matrices internally, then the per-part split format).
+// Throws std::runtime_error on bad input; the C ABI catches.
+void build_hierarchy(const Csr& A, const std::vector<int32_t>& owner, int32_t nparts,
+                     const pamg_options& o, Hierarchy& h);
+// halo plans from the index maps of all parts of a level (also used for external hierarchies)
+void build_halo_plans(Level& lev, int32_t nparts);
+void finalize_external(Hierarchy& h);
+
+}  // namespace pamg
