@@ -26,7 +26,7 @@ namespace pamg {
 constexpr int RED_W = 4;  // doubles per all-reduce slot
 constexpr int MAX_LEVELS = 16;
 constexpr int BLOCK = 256;
-constexpr unsigned long long SPIN_TIMEOUT_NS = 5000000000ull;  // 5 s, then flag an error and fall through
+constexpr unsigned long long SPIN_TIMEOUT_NS = 2000000000ull;  // 2 s, then flag an error and fall through
 
 enum Mode : int { M_MUL = 0, M_RESID = 1, M_JACOBI = 2, M_ADD = 3, M_RESTRICT = 4, M_CHEB = 5 };
 
@@ -111,10 +111,13 @@ __device__ __forceinline__ int32_t ldg_stream(const int32_t* p) { return __ldcs(
 
 __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t e, DevState* st) {
   if ((int32_t)(ld_acquire_sys(flag) - e) >= 0) return;
+  if (*(volatile int32_t*)&st->error) return;  // a wait already timed out: fail fast, the host reports it
   const unsigned long long t0 = globaltimer_ns();
   while ((int32_t)(ld_acquire_sys(flag) - e) < 0) {
+    if (*(volatile int32_t*)&st->error) return;
     if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
       st->error = 1;
+      __threadfence();
       return;
     }
     __nanosleep(64);
@@ -286,8 +289,16 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
   const int lane = threadIdx.x % LANES;
   const int grp = threadIdx.x / LANES;
   double acc = 0.0;
-  for (int r = blockIdx.x * RPB + grp; r < A.nrows; r += gridDim.x * RPB) {
-    const int beg = A.ptr[r], end = A.ptr[r + 1];
+  // block-uniform trip count: every lane of a warp reaches the full-mask shuffles below, rows past
+  // the end are just predicated off (a lane that skipped the loop would deadlock the shuffle)
+  for (int r0 = blockIdx.x * RPB; r0 < A.nrows; r0 += gridDim.x * RPB) {
+    const int r = r0 + grp;
+    const bool valid = r < A.nrows;
+    int beg = 0, end = 0;
+    if (valid) {
+      beg = A.ptr[r];
+      end = A.ptr[r + 1];
+    }
     double s = 0.0;
     for (int k = beg + lane; k < end; k += LANES) {
       const int c = ldg_stream(A.col + k);
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
       s += v * (OG ? __ldcv(x + c) : x[c]);
     }
     s = group_sum<LANES>(s);
-    if (lane == 0) {
+    if (valid && lane == 0) {
       const int row = A.rows ? A.rows[r] : r;
       const double res = apply_epilogue<MODE, OG>(a, row, s);
       if (DOT) acc += a.dotv[row] * res;

@@ -1,0 +1,189 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every kernel, the V-cycle and PCG against
+the oracle on the SAME operators (the oracle-built hierarchy is uploaded through
+pamg_level_upload), through the C ABI.  fp64 tolerances are the ones BASELINE.json north_star
+states: 1e-12 relative per V-cycle, identical PCG iteration counts at rtol 1e-8."""
+import numpy as np
+import pytest
+
+import amg_oracle as O
+from parallel_amg_b200 import _lib as L
+from util import (det_vector, oracle_problem, own_of, own_parts, product_context_from_oracle, product_options, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+TOL_KERNEL = 1e-13   # one SpMV-shaped pass
+TOL_VCYCLE = 1e-12   # north_star: per V-cycle, fp64
+
+# (dims, parts): 1 part = plain single GPU; >1 parts share cuda:0 (debug-backend layout)
+PROBLEMS = [((20, 20, 20), (1, 1, 1)), ((20, 20, 20), (2, 2, 2)), ((33, 31, 17), (3, 2, 1)), ((200, 200), (2, 2))]
+
+
+def make(dims, pp, oopts=None, **extra):
+    A, owner, h = oracle_problem(dims, pp, tuple(sorted((oopts or {}).items())))
+    c = product_context_from_oracle(h, oopts, **extra)
+    c.device_init()
+    return A, h, c
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+def test_spmv_every_level(dims, pp):
+    A, h, c = make(dims, pp)
+    for l, lev in enumerate(h["levels"]):
+        n = h["global"]["levels"][l]["A"].shape[0]
+        x = det_vector(n, 11 + l)
+        ref = own_of(lev, O.spmv(lev, O.pvector_from_global(lev, x)))
+        got = c.spmv(l, own_parts(lev, x))
+        assert rel_err(got, ref) <= TOL_KERNEL
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+def test_spmv_all_lane_widths(lanes):
+    A, h, c = make((20, 20, 20), (2, 1, 1), None, lanes_per_row=lanes)
+    lev = h["levels"][0]
+    x = det_vector(A.shape[0], 3)
+    ref = own_of(lev, O.spmv(lev, O.pvector_from_global(lev, x)))
+    assert rel_err(c.spmv(0, own_parts(lev, x)), ref) <= TOL_KERNEL
+    assert c.stats().lanes[0] == lanes
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS[:3])
+@pytest.mark.parametrize("smoother", ["jacobi", "l1jacobi", "chebyshev"])
+def test_smoother_sweeps(dims, pp, smoother):
+    oopts = {"smoother": smoother}
+    A, h, c = make(dims, pp, oopts)
+    for l, lev in enumerate(h["levels"][:-1]):
+        n = h["global"]["levels"][l]["A"].shape[0]
+        b, x0 = det_vector(n, 21 + l), det_vector(n, 31 + l)
+        for nu in (1, 2):
+            ref = O.smooth(h, l, O.pvector_from_global(lev, x0), O.pvector_from_global(lev, b), nu)
+            got = c.smooth(l, nu, own_parts(lev, b), own_parts(lev, x0))
+            assert rel_err(got, own_of(lev, ref)) <= 4 * TOL_KERNEL
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+def test_residual_restrict_and_prolong_correct(dims, pp):
+    A, h, c = make(dims, pp)
+    for l in range(len(h["levels"]) - 1):
+        lev, nxt = h["levels"][l], h["levels"][l + 1]
+        n = h["global"]["levels"][l]["A"].shape[0]
+        nc = h["global"]["levels"][l + 1]["A"].shape[0]
+        b, x, ec = det_vector(n, 41), det_vector(n, 42), det_vector(nc, 43)
+        gl = h["global"]["levels"][l]
+        r_ref = b - gl["A"] @ x
+        bc_ref = gl["R"] @ r_ref
+        r, bc = c.residual_restrict(l, own_parts(lev, b), own_parts(lev, x))
+        assert rel_err(r, own_parts(lev, r_ref)) <= TOL_KERNEL
+        assert rel_err(bc, own_parts(nxt, bc_ref)) <= 4 * TOL_KERNEL
+        x_ref = x + gl["P"] @ ec
+        got = c.prolong_correct(l, own_parts(nxt, ec), own_parts(lev, x))
+        assert rel_err(got, own_parts(lev, x_ref)) <= TOL_KERNEL
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS[:3])
+def test_dot_consistent_assemble(dims, pp):
+    A, h, c = make(dims, pp)
+    for l, lev in enumerate(h["levels"]):
+        n = h["global"]["levels"][l]["A"].shape[0]
+        u, v = det_vector(n, 51), det_vector(n, 52)
+        assert abs(c.dot(l, own_parts(lev, u), own_parts(lev, v)) - float(u @ v)) <= 1e-13 * np.abs(u * v).sum()
+        # consistent!: ghosts <- owners, bit-exact copies
+        loc = [np.concatenate([u[d["own_to_global"]], np.full(len(d["ghost_to_global"]), np.nan)]) for d in lev["parts"]]
+        c.consistent(l, loc)
+        for d, a in zip(lev["parts"], loc):
+            assert np.array_equal(a[len(d["own_to_global"]):], u[d["ghost_to_global"]])
+        # assemble!: owners += ghost copies, ghosts <- 0 (same order as the oracle => bit-exact)
+        ws = [det_vector(len(d["own_to_global"]) + len(d["ghost_to_global"]), 60 + p) for p, d in enumerate(lev["parts"])]
+        ref = O.assemble(lev, [w.copy() for w in ws])
+        c.assemble(l, ws)
+        for a, b_ in zip(ws, ref):
+            assert np.allclose(a, b_, rtol=0, atol=1e-15 * 8)
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+@pytest.mark.parametrize("oopts", [{}, {"nu_pre": 2, "nu_post": 2}, {"smoother": "l1jacobi"},
+                                   {"smoother": "chebyshev", "cheb_degree": 3}, {"nu_pre": 0, "nu_post": 2}],
+                         ids=["jacobi11", "jacobi22", "l1", "cheb3", "post-only"])
+def test_vcycle_parity(dims, pp, oopts):
+    A, h, c = make(dims, pp, oopts)
+    lev = h["levels"][0]
+    n = A.shape[0]
+    for seed in (71, 72):
+        b = det_vector(n, seed)
+        ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+        got = c.vcycle(own_parts(lev, b))
+        assert rel_err(got, ref) <= TOL_VCYCLE
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+@pytest.mark.parametrize("oopts", [{}, {"smoother": "chebyshev", "cheb_degree": 2}], ids=["jacobi", "cheb2"])
+def test_pcg_iteration_count_and_history(dims, pp, oopts):
+    A, h, c = make(dims, pp, oopts)
+    lev = h["levels"][0]
+    n = A.shape[0]
+    for b in (A @ np.ones(n) + det_vector(n, 81), det_vector(n, 82)):
+        xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, b))
+        x, it, hist, ok = c.pcg(own_parts(lev, b), rtol=1e-8, maxiter=200)
+        assert ok and it == it_ref
+        assert np.allclose(hist, hist_ref, rtol=1e-7)
+        assert rel_err(x, own_of(lev, xs)) <= 1e-10
+        xg = np.zeros(n)
+        for d, xp in zip(lev["parts"], x):
+            xg[d["own_to_global"]] = xp
+        assert np.linalg.norm(b - A @ xg) <= 1.0001e-8 * np.linalg.norm(b)
+
+
+def test_pcg_graph_and_eager_agree_bitwise():
+    A, h, c1 = make((20, 20, 20), (2, 2, 2), None, use_graph=1)
+    _, _, c0 = make((20, 20, 20), (2, 2, 2), None, use_graph=0)
+    lev = h["levels"][0]
+    b = det_vector(A.shape[0], 91)
+    x1, it1, h1, _ = c1.pcg(own_parts(lev, b))
+    x0, it0, h0, _ = c0.pcg(own_parts(lev, b))
+    assert it1 == it0 and np.array_equal(h1, h0)
+    assert all(np.array_equal(a, b_) for a, b_ in zip(x1, x0))
+    # a second solve on the same context replays the same graph and reproduces the same bits
+    x2, it2, h2, _ = c1.pcg(own_parts(lev, b))
+    assert it2 == it1 and all(np.array_equal(a, b_) for a, b_ in zip(x1, x2))
+    assert c1.stats().kernel_launches > 0
+
+
+def test_pcg_edge_cases():
+    A, h, c = make((20, 20, 20), (1, 1, 1))
+    lev = h["levels"][0]
+    n = A.shape[0]
+    x, it, hist, ok = c.pcg([np.zeros(n)])                     # zero rhs: 0 iterations, x = 0
+    assert ok and it == 0 and np.all(x[0] == 0.0)
+    x, it, hist, ok = c.pcg([det_vector(n, 5)], maxiter=3)     # maxiter hit: reported, not raised
+    assert (not ok) and it == 3 and len(hist) == 4
+    xs, it_ref, _ = O.pcg(h, O.pvector_from_global(lev, det_vector(n, 5)), precond=False, maxiter=500)
+    x, it, hist, ok = c.pcg([det_vector(n, 5)], precond=False, maxiter=500)   # plain CG path
+    assert ok and it == it_ref
+
+
+def test_single_level_hierarchy_is_a_direct_solve():
+    A, h, c = make((7, 5), (1, 1))
+    b = det_vector(35, 7)
+    x, it, hist, ok = c.pcg([b])
+    assert ok and it <= 2
+    assert np.linalg.norm(A @ x[0] - b) <= 1e-8 * np.linalg.norm(b)
+
+
+def test_product_setup_solves_config2_shape_and_is_symmetric_preconditioner():
+    """Product host setup + device solve at a size the oracle does not need to touch:
+    size-independent properties (true residual, symmetry of the V-cycle operator, linearity)."""
+    dims = (64, 64, 64)
+    c = L.Context(1)
+    c.gallery_poisson(dims, (1, 1, 1))
+    c.setup()
+    c.device_init()
+    n = 64 ** 3
+    b = c.host_matvec_global(np.ones(n))
+    x, it, hist, ok = c.pcg([b])
+    assert ok and hist[-1] <= 1e-8 * hist[0]
+    assert np.linalg.norm(c.host_matvec_global(x[0]) - b) <= 1.001e-8 * np.linalg.norm(b)
+    assert np.abs(x[0] - 1.0).max() <= 1e-6
+    u, v = det_vector(n, 1), det_vector(n, 2)
+    Mu, Mv = c.vcycle([u])[0], c.vcycle([v])[0]
+    assert abs(v @ Mu - u @ Mv) <= 1e-10 * abs(v @ Mu)          # M symmetric (nu_pre == nu_post)
+    Muv = c.vcycle([2.0 * u - 3.0 * v])[0]
+    assert np.linalg.norm(Muv - (2.0 * Mu - 3.0 * Mv)) <= 1e-12 * np.linalg.norm(Muv)   # linear
