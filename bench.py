@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — AMG-PCG solve throughput (DOF/s) on N B200s, plus roofline / CPU baseline / e2e.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload poisson3d-256|poisson3d-128]
+  python bench.py --impl reference ...     # the CPU oracle port timed on the host cores
+
+A "step" is one whole AMG-preconditioned CG solve (x0 = 0, b = A*xstar, to ||r|| <= 1e-8 ||r0||) of
+BASELINE.json configs[2] (3-D Poisson 7-point 256^3, strong-scaled over N = 1/2/4/8 GPUs as
+(1,1,1)/(2,1,1)/(2,2,1)/(2,2,2) Cartesian blocks).  The hierarchy is built on the host and uploaded
+once (outside the timed region, as the north star prescribes).  `value` times K solves with b
+resident in HBM (CUDA events inside the library, max over ranks); `e2e` times the same solves
+through the C-ABI call pamg_pcg with pinned HOST buffers (H2D of b, D2H of x inside the region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "poisson3d-256": dict(dims=(256, 256, 256), desc="3D Poisson 7-point 256^3 (16.7M DOF), b=A*xstar, x0=0, rtol 1e-8"),
+    "poisson3d-128": dict(dims=(128, 128, 128), desc="3D Poisson 7-point 128^3 (2.1M DOF), b=A*xstar, x0=0, rtol 1e-8"),
+    "poisson3d-64": dict(dims=(64, 64, 64), desc="3D Poisson 7-point 64^3 (262k DOF), b=A*xstar, x0=0, rtol 1e-8"),
+}
+PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+RTOL, MAXITER = 1e-8, 200
+
+
+def xstar(n):
+    """Known solution of the benchmark system: deterministic pseudo-random values in (-1, 1)
+    (multiplicative hash of the gid, identical bits everywhere).  SURVEY.md 8d proposed b = A*1, but
+    that right-hand side is degenerate for this hierarchy (PCG converges in ONE iteration at 32^3 and
+    128^3), so it would not measure a solve; see DESIGN.md "Benchmark right-hand side"."""
+    i = np.arange(n, dtype=np.uint64)
+    return ((i * np.uint64(2654435761) + np.uint64(40503)) % np.uint64(2 ** 32)).astype(np.float64) / 2.0 ** 31 - 1.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def pull_levels(c, nparts):
+    """Copy the product-built hierarchy out through the C ABI into the layout the C oracle takes."""
+    from types import SimpleNamespace
+    from parallel_amg_b200 import _lib as L
+    nl = c.num_levels()
+    levels = []
+    for l in range(nl):
+        parts = []
+        for p in range(nparts):
+            own, gh, gho = c.index_maps(l, p)
+            d = dict(own_to_global=own, ghost_to_global=gh, ghost_to_owner=gho)
+            for b, name in enumerate(L.BLOCK_NAMES):
+                if l == nl - 1 and b >= L.P_OO:
+                    continue
+                ip, ix, dd = c.block(l, p, b)
+                d[name] = SimpleNamespace(indptr=ip, indices=ix, data=dd)
+            dg, _ = c.diag(l, p)
+            d["w"] = (2.0 / 3.0) / dg
+            parts.append(d)
+        levels.append(parts)
+    return levels, c.coarse_inverse()
+
+
+def cpu_solve_timed(c, nparts, b_parts, reps):
+    """The oracle's C/OpenMP solve phase on the host cores, same hierarchy, same rhs."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    levels, inv = pull_levels(c, nparts)
+    co = c_oracle.COracle(levels, inv, 1, 1)
+    times, it = [], 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        x, it, hist = co.pcg(b_parts, RTOL, MAXITER, True)
+        times.append(time.perf_counter() - t0)
+    co.close()
+    return times, it, hist
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: there is no reference code to run and no Julia; the arm times
+    the CPU oracle port (oracle/pamg_oracle.c) with all host threads on the same config."""
+    if rank != 0:
+        return
+    from parallel_amg_b200 import _lib as L
+    nparts = args.gpus
+    c = L.Context(nparts)
+    dims = wl["dims"]
+    c.gallery_poisson(dims, PARTS[nparts])
+    c.setup()
+    n, nnz = c.global_size()
+    b = c.host_matvec_global(xstar(n))
+    b_parts = [b[c.index_maps(0, p)[0]] for p in range(nparts)]
+    times, it, hist = cpu_solve_timed(c, nparts, b_parts, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = float(sum(timed))
+    cores = os.cpu_count()
+    val = n * len(timed) / total
+    line = dict(impl="reference", metric="amg_pcg_solve_dof_per_s", value=val, unit="DOF/s", n_gpus=args.gpus, steps=len(timed),
+                warmup=args.warmup, ms_per_step=1e3 * total / len(timed), higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=args.workload, description=wl["desc"], parts=list(PARTS[nparts]), iters=int(it),
+                            note="no reference code exists (README+LICENSE only) and Julia is absent: this is the repo's C/OpenMP "
+                                 "oracle port of the same algorithm on the same hierarchy (built by the host setup, bit-exact vs the "
+                                 "oracle setup in tests)"),
+                cpu_baseline=dict(value=val, unit="DOF/s", cores=cores, kind="port", sample="whole solve, every step",
+                                  omp_threads=int(os.environ.get("OMP_NUM_THREADS", cores))),
+                e2e=dict(value=val, unit="DOF/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="poisson3d-256", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--smoother", default="jacobi")
+    args = ap.parse_args()
+    if args.gpus not in PARTS:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}: launch with torchrun --nproc-per-node {args.gpus}")
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from parallel_amg_b200 import _lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the product path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nparts = args.gpus
+    dims = wl["dims"]
+    c = L.Context(nparts)
+    t0 = time.perf_counter()
+    c.gallery_poisson(dims, PARTS[nparts])
+    # host setup is replicated on every rank (deterministic); run it in waves so that the box's memory
+    # holds the concurrent copies (256^3 needs ~13 GB per process while building)
+    if world > 1:
+        try:
+            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+        except Exception:
+            avail = 64 << 30
+        need = 1000 * int(np.prod(dims))  # bytes, generous
+        per_wave = max(1, min(world, int(0.6 * avail // need)))
+        for w0 in range(0, world, per_wave):
+            if w0 <= rank < w0 + per_wave:
+                c.setup(c.default_options())
+            dist.barrier()
+    else:
+        c.setup(c.default_options())
+    setup_s = time.perf_counter() - t0
+    n, nnz = c.global_size()
+    if world > 1:
+        c.device_init([rank], [local_rank])
+        blobs = [None] * world
+        dist.all_gather_object(blobs, c.comm_export(rank))
+        for p, bl in enumerate(blobs):
+            if p != rank:
+                c.comm_import(p, bl)
+        c.comm_connect()
+        mine = [rank]
+    else:
+        c.device_init([0], [local_rank])
+        mine = [0]
+    xs_true = xstar(n)
+    b = c.host_matvec_global(xs_true)
+    own = {p: c.index_maps(0, p)[0] for p in mine}
+    # pinned host buffers for the e2e leg (the library copies from/to these pointers)
+    b_pin = {p: torch.from_numpy(b[own[p]].copy()).pin_memory() for p in mine}
+    b_parts = [b_pin[p].numpy() if p in b_pin else None for p in range(nparts)]
+    n_local = sum(len(own[p]) for p in mine)
+
+    # ---- value: K solves with b resident in HBM ---------------------------------------------
+    c.load_rhs(b_parts)
+    for _ in range(args.warmup):
+        it, hist, ok = c.pcg_resident(RTOL, MAXITER, True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, launches = 0.0, 0
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        it, hist, ok = c.pcg_resident(RTOL, MAXITER, True)
+        st = c.stats()
+        dev_ms += st.solve_ms
+        launches += st.kernel_launches
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks = sampler.stop() if rank == 0 else None
+    assert ok, "PCG did not converge"
+    x = c.read_solution()
+    # true-residual check of the timed result (size-independent property): ||b - A x|| <= rtol ||b||
+    xg = np.zeros(n)
+    for p in mine:
+        xg[own[p]] = x[p]
+    if world > 1:
+        t = torch.from_numpy(xg).cuda()
+        dist.all_reduce(t)
+        xg = t.cpu().numpy()
+    true_rel = float(np.linalg.norm(b - c.host_matvec_global(xg)) / np.linalg.norm(b))
+    assert true_rel <= 2e-8, f"true residual {true_rel}"
+    sol_err = float(np.abs(xg - xs_true).max())
+
+    # ---- e2e: the C-ABI call with host buffers (H2D b, D2H x inside the timed region) ---------
+    for _ in range(2):
+        c.pcg(b_parts, RTOL, MAXITER, True)
+    barrier()
+    t_e2e = time.perf_counter()
+    for _ in range(args.steps):
+        xh, it2, hist2, ok2 = c.pcg(b_parts, RTOL, MAXITER, True)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t_e2e)
+
+    # ---- V-cycle ms and per-kernel roofline (CUDA events on the library's stream) --------------
+    vc = c.time_kernel(5, 0, 23, False)[3:]
+    kern = {}
+    info = c.level_info(0, mine[0])
+    n_own, nnz_oo = info.n_own, info.nnz[0]
+    nnz_p = info.nnz[2]
+    spmv_bytes = 12 * nnz_oo + 4 * (n_own + 1) + 8 * n_own + 8 * n_own
+    algo = {0: ("spmv A0 (k_spmv MUL)", spmv_bytes), 1: ("jacobi sweep A0 (k_spmv JACOBI)", spmv_bytes + 16 * n_own)}
+    for kind, (name, nbytes) in algo.items():
+        ms = c.time_kernel(kind, 0, 13, True)[3:]
+        kern[name] = dict(ms=float(np.mean(ms)), gbs=nbytes / (float(np.mean(ms)) * 1e-3) / 1e9, bytes=int(nbytes))
+    lanes = c.stats().lanes[0]
+
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_ms = [float(v) for v in t.cpu()]
+        tl = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tl)
+        launches = int(tl.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        dom = kern["spmv A0 (k_spmv MUL)"]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get("spmv_A0_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = dict(
+            metric="amg_pcg_solve_dof_per_s", value=n * args.steps / (dev_ms * 1e-3), unit="DOF/s", n_gpus=args.gpus,
+            steps=args.steps, warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="strong",
+            vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=args.workload, description=wl["desc"], parts=list(PARTS[nparts]), iters=int(it),
+                        levels=c.num_levels(), smoother="jacobi(2/3) 1+1", l2="working set >> 126 MB L2 (no flush needed)",
+                        timing="CUDA events inside libpamg around each solve, summed over steps, max over ranks",
+                        host_setup_s=round(setup_s, 1)),
+            vcycle_ms=float(np.mean(vc)), wall_ms_per_step=wall_ms / args.steps, true_residual_rel=true_rel, solution_max_err=sol_err,
+            roofline=dict(bound="hbm", kernel=f"k_spmv<lanes={lanes},MUL> level 0 (y = A x, fp64 CSR int32)", achieved=dom["gbs"],
+                          peak=peak, unit="GB/s", frac=dom["gbs"] / peak, peak_source=peak_src, traffic=traffic,
+                          algorithmic_bytes_per_launch=dom["bytes"], ms_per_launch=dom["ms"],
+                          frac_of_nominal_8TBs=dom["gbs"] / 8000.0),
+            kernels=kern,
+            e2e=dict(value=n * args.steps / (e2e_ms * 1e-3), unit="DOF/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
+                     ms_per_step=e2e_ms / args.steps),
+            gpu_launches=int(launches), clocks=clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            times, it_cpu, _ = cpu_solve_timed(c, nparts, [b[own[0]]], 2)
+            cores = os.cpu_count()
+            line["cpu_baseline"] = dict(value=n / min(times), unit="DOF/s", cores=cores, kind="port",
+                                        sample=f"2 whole solves ({it_cpu} iterations each) of the same workload, best of 2; "
+                                               "C/OpenMP oracle port (no reference code exists)",
+                                        seconds=[round(t, 3) for t in times], iters=int(it_cpu))
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        c.close()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

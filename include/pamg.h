@@ -39,7 +39,11 @@ typedef enum {
 } pamg_status;
 
 enum { PAMG_SMOOTHER_JACOBI = 0, PAMG_SMOOTHER_L1JACOBI = 1, PAMG_SMOOTHER_CHEBYSHEV = 2 };
-enum { PAMG_FORMAT_AUTO = 0, PAMG_FORMAT_CSR = 1, PAMG_FORMAT_SELL = 2 };
+/* kernel family for the own-own blocks: CSR = sub-warp "vector per row" (1..32 lanes chosen from the
+ * mean nnz/row; 32 = warp per row); STREAM = CSR-stream (block-cooperative 128-bit coalesced loads of
+ * the contiguous val/col ranges, products staged in shared memory).  AUTO picks STREAM whenever every
+ * row fits the product buffer, else CSR.  The storage is plain CSR for both. */
+enum { PAMG_FORMAT_AUTO = 0, PAMG_FORMAT_CSR = 1, PAMG_FORMAT_STREAM = 2 };
 /* blocks of the split (own/ghost) storage of a level, PSparseMatrix own_own_values /
  * own_ghost_values (SURVEY.md App. A "PSparseMatrix") */
 enum { PAMG_A_OO = 0, PAMG_A_OG = 1, PAMG_P_OO = 2, PAMG_P_OG = 3, PAMG_R_OO = 4, PAMG_R_OG = 5 };
@@ -57,7 +61,7 @@ typedef struct {
   int32_t cheb_degree;
   double cheb_lo_frac;    /* Chebyshev interval [lo_frac*rho, hi_frac*rho] of D^-1 A */
   double cheb_hi_frac;
-  int32_t spmv_format;    /* PAMG_FORMAT_* ; AUTO picks per level from the nnz/row histogram */
+  int32_t spmv_format;    /* PAMG_FORMAT_* ; AUTO decides per level and per operator (A, P, R) */
   int32_t use_graph;      /* 1: replay the V-cycle / PCG iteration as CUDA graphs */
   int32_t lanes_per_row;  /* 0: auto (from mean nnz/row); else 1,2,4,8,16,32 for CSR */
   int32_t tail_rows;      /* levels whose global rows <= this run inside one fused tail kernel (0: off) */

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libpamg.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOGPU, ERR_COMM, ERR_NOTCONV, ERR_ALLOC = 0, -1, -2, -3, -4, -5, -6
 SMOOTHER_JACOBI, SMOOTHER_L1JACOBI, SMOOTHER_CHEBYSHEV = 0, 1, 2
+FORMAT_AUTO, FORMAT_CSR, FORMAT_STREAM = 0, 1, 2
 A_OO, A_OG, P_OO, P_OG, R_OO, R_OG = range(6)
 BLOCK_NAMES = ("A_oo", "A_og", "P_oo", "P_og", "R_oo", "R_og")
 

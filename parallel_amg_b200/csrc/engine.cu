@@ -64,7 +64,12 @@ struct DevCsr {
   bool listed = false;
   int64_t nnz = 0;
   int lanes = 8;
+  // CSR-stream row blocks (own-own blocks only)
+  DBuf<int2> blk;
+  int nblocks = 0;
+  bool stream = false;
   CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
+  StreamView sview() const { return StreamView{blk.p, ptr.p, col.p, val.p, nrows, nblocks}; }
 };
 
 int pick_lanes(double mean) {
@@ -76,7 +81,7 @@ int pick_lanes(double mean) {
   return 32;
 }
 
-void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override) {
+void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, bool want_stream) {
   const int64_t nr = m.nrows;
   std::vector<int32_t> ptr;
   d.listed = compress;
@@ -85,9 +90,10 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override) 
     d.nrows = compress ? 0 : (int32_t)nr;
     ptr.assign((compress ? 0 : nr) + 1, 0);
     d.ptr.upload(ptr);
-    d.col.alloc(0);
-    d.val.alloc(0);
+    d.col.alloc(16);
+    d.val.alloc(16);
     d.rows.alloc(0);
+    d.stream = false;
     return;
   }
   if (compress) {
@@ -107,10 +113,42 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override) 
     d.rows.alloc(0);
   }
   d.ptr.upload(ptr);
-  d.col.upload(m.col);
-  d.val.upload(m.val);
+  {  // pad to a multiple of 4 entries (+8) with zeros: the stream kernel reads whole 128-bit groups
+    const size_t padded = (m.col.size() + 3) / 4 * 4 + 8;
+    std::vector<int32_t> col(m.col);
+    std::vector<double> val(m.val);
+    col.resize(padded, 0);
+    val.resize(padded, 0.0);
+    d.col.upload(col);
+    d.val.upload(val);
+  }
   const double mean = d.nrows ? (double)d.nnz / d.nrows : 0.0;
   d.lanes = lanes_override > 0 ? lanes_override : pick_lanes(mean);
+  d.stream = false;
+  d.nblocks = 0;
+  if (want_stream && !compress && nr > 0) {
+    // greedy row blocks: <= S_ROWS rows and <= S_CAP - 3 entries (so the 4-aligned window fits)
+    std::vector<int2> blk;
+    int64_t r = 0;
+    bool ok = true;
+    while (r < nr) {
+      const int64_t e0 = m.ptr[r];
+      int64_t r1 = r;
+      while (r1 < nr && r1 - r < S_ROWS && m.ptr[r1 + 1] - e0 <= S_CAP - 3) ++r1;
+      if (r1 == r) {  // a single row exceeds the product buffer: keep the vector kernel for this matrix
+        ok = false;
+        break;
+      }
+      blk.push_back(make_int2((int)r, (int)e0));
+      r = r1;
+    }
+    if (ok) {
+      blk.push_back(make_int2((int)nr, (int)m.ptr[nr]));
+      d.nblocks = (int)blk.size() - 1;
+      d.blk.upload(blk);
+      d.stream = true;
+    }
+  }
 }
 
 // byte offsets inside a part's peer-visible arena; computable by every process for every part
@@ -306,6 +344,31 @@ void launch_spmv_mode(int mode, int lanes, int grid, cudaStream_t s, CsrView A, 
 #undef PAMG_M
 }
 
+void launch_stream(int mode, bool dot, int grid, cudaStream_t s, StreamView A, const double* x, const EpiArgs& a, DevState* st,
+                   double* partials, const RedCtx& rc, int publish, int slot) {
+#define PAMG_S(MD, DT)                                                                      \
+  k_spmv_stream<MD, DT><<<grid, BLOCK, 0, s>>>(A, x, a, st, partials, rc, publish, slot); \
+  break;
+  if (dot) {
+    switch (mode) {
+      case M_MUL: PAMG_S(M_MUL, true)
+      case M_JACOBI: PAMG_S(M_JACOBI, true)
+      default: throw std::runtime_error("fused dot only on MUL/JACOBI");
+    }
+  } else {
+    switch (mode) {
+      case M_MUL: PAMG_S(M_MUL, false)
+      case M_RESID: PAMG_S(M_RESID, false)
+      case M_JACOBI: PAMG_S(M_JACOBI, false)
+      case M_ADD: PAMG_S(M_ADD, false)
+      case M_RESTRICT: PAMG_S(M_RESTRICT, false)
+      case M_CHEB: PAMG_S(M_CHEB, false)
+      default: throw std::runtime_error("bad mode");
+    }
+  }
+#undef PAMG_S
+}
+
 }  // namespace
 
 // One SpMV-family operation over all local parts:  [pack halo of xin] ; main (own-own) ; [own-ghost correction].
@@ -348,6 +411,12 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     const DevCsr& m = ld.blk[op.which];
     const bool og_follows = need && hl.n_recv_nbrs > 0;
     I.set_dev(pd);
+    if (m.stream) {
+      launch_stream(op.mode, op.dot, m.nblocks, pd.stream, m.sview(), xin[i], epi[i], pd.st.p, pd.partials.p, pd.rc,
+                    og_follows ? 0 : 1, op.slot);
+      I.note_launch();
+      continue;
+    }
     const int rpb = BLOCK / m.lanes;
     const int grid = I.grid_for(m.nrows, rpb * 4);
     if (op.dot)
@@ -435,8 +504,8 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     CK(cudaMemset(pd.arena, 0, pd.lay.total));
     I.arena_of[part] = pd.arena;
     pd.st.alloc(1);
-    pd.partials.alloc(Impl::MAX_GRID + 64);
     pd.scratch4.alloc(RED_W);
+    int max_blocks = Impl::MAX_GRID;
 
     for (int l = 0; l < I.L; ++l) {
       const PartLevel& pl = h->levels[l].parts[part];
@@ -448,7 +517,8 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         const bool og = (b & 1);
         int lanes = 0;
         if (!og && b == PAMG_A_OO && o.lanes_per_row > 0) lanes = o.lanes_per_row;
-        build_csr(pl.blk[b], og, ld.blk[b], og ? 4 : lanes);
+        build_csr(pl.blk[b], og, ld.blk[b], og ? 4 : lanes, !og && o.spmv_format != PAMG_FORMAT_CSR);
+        max_blocks = std::max(max_blocks, ld.blk[b].nblocks);
       }
       // smoother weights
       std::vector<double> w(pl.n_own), dinv(pl.n_own);
@@ -502,6 +572,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         ld.asm_flags = (const uint32_t*)(pd.arena + pd.lay.asm_flags[l]);
       }
     }
+    pd.partials.alloc((size_t)max_blocks + 64);  // one partial per CTA of a fused-reduction kernel
     // coarsest solve data
     const PartLevel& pc = h->levels[I.L - 1].parts[part];
     pd.inv.upload(h->coarse_inv);
@@ -1456,7 +1527,7 @@ void Engine::get_stats(pamg_stats* s) {
   *s = I.stats;
   s->n_levels = I.L;
   for (int l = 0; l < 16; ++l) {
-    s->format[l] = l < I.L ? PAMG_FORMAT_CSR : 0;
+    s->format[l] = (l < I.L && !I.parts.empty()) ? (I.P(0).lev[l]->blk[PAMG_A_OO].stream ? PAMG_FORMAT_STREAM : PAMG_FORMAT_CSR) : 0;
     s->lanes[l] = (l < I.L && !I.parts.empty()) ? I.P(0).lev[l]->blk[PAMG_A_OO].lanes : 0;
   }
 }

@@ -316,6 +316,119 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// CSR-stream SpMV family (the fast path for the own-own blocks).
+//
+// The vector kernel above is latency-bound on short rows (ncu, profiles/r01: ~18 % DRAM
+// throughput at full occupancy, long-scoreboard stalls: a serial ptr -> col/val -> x chain with
+// ~12 B in flight per thread).  Here a CTA owns a run of consecutive rows whose entries fit the
+// shared-memory product buffer; the run's val/col ranges are CONTIGUOUS in CSR, so phase A streams
+// them with fully coalesced 128-bit loads (int4 of 4 column ids + 2 x double2 of values per thread
+// and step, all steps issued back to back: up to 144 B in flight per thread), gathers x through
+// L1/L2 and parks the products in shared memory; phase B sums each row's products in column order
+// (one thread per row) and applies the fused epilogue, whose operands were prefetched before
+// phase A.  Products are rounded before they are added (no FMA across the smem round trip), so a
+// row sum is bit-identical to the oracle's sequential `s += a_ij * x_j`.
+// ---------------------------------------------------------------------------------------------
+constexpr int S_CAP = 3072;   // entries per CTA (24 KB of fp64 products)
+constexpr int S_ROWS = BLOCK; // at most one row per thread in phase B
+constexpr int S_STEPS = (S_CAP + 4 * BLOCK - 1) / (4 * BLOCK);
+
+struct StreamView {
+  const int2* blk;     // [nblocks + 1] {first row, first entry} of each row block
+  const int32_t* ptr;
+  const int32_t* col;  // padded with zeros to a multiple of 4 entries (+ 8)
+  const double* val;
+  int32_t nrows, nblocks;
+};
+
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK) k_spmv_stream(StreamView A, const double* __restrict__ x, EpiArgs a, DevState* st,
+                                                        double* partials, RedCtx rc, int publish, int red_slot) {
+  if (st->done) return;
+  __shared__ double prod[S_STEPS * 4 * BLOCK];
+  const int t = threadIdx.x;
+  const int2 b0 = A.blk[blockIdx.x], b1 = A.blk[blockIdx.x + 1];
+  const int r0 = b0.x, nr = b1.x - b0.x;
+  const int ea = b0.y & ~3;              // 4-entry aligned start: 16 B (col) / 32 B (val) aligned
+  const int n4 = (b1.y - ea + 3) >> 2;   // 4-entry groups to stream (<= S_STEPS * BLOCK by construction)
+  const int row = r0 + t;
+  const bool active = t < nr;
+  // prefetch row extents and epilogue operands; their latency overlaps phase A
+  int pb = 0, pe = 0;
+  double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0, e_dot = 0.0;
+  if (active) {
+    pb = A.ptr[row] - ea;
+    pe = A.ptr[row + 1] - ea;
+    if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
+    if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
+    if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
+    if (MODE == M_CHEB && a.aux) e_aux = a.aux[row];
+    if (DOT) e_dot = a.dotv[row];
+  }
+  // phase A: stream entries [ea, ea + 4 n4).  Entries outside the block's own range belong to the
+  // neighbouring blocks (or the zero padding): valid data, their products are simply never read.
+  const int4* __restrict__ col4 = reinterpret_cast<const int4*>(A.col + ea);
+  const double2* __restrict__ val2 = reinterpret_cast<const double2*>(A.val + ea);
+  int4 c[S_STEPS];
+  double2 v0[S_STEPS], v1[S_STEPS];
+#pragma unroll
+  for (int j = 0; j < S_STEPS; ++j) {
+    const int g = t + j * BLOCK;
+    if (g < n4) {
+      c[j] = __ldcs(col4 + g);
+      v0[j] = __ldcs(val2 + 2 * g);
+      v1[j] = __ldcs(val2 + 2 * g + 1);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < S_STEPS; ++j) {
+    const int g = t + j * BLOCK;
+    if (g < n4) {
+      const double x0 = x[c[j].x], x1 = x[c[j].y], x2 = x[c[j].z], x3 = x[c[j].w];
+      double2 p0, p1;
+      p0.x = v0[j].x * x0;
+      p0.y = v0[j].y * x1;
+      p1.x = v1[j].x * x2;
+      p1.y = v1[j].y * x3;
+      reinterpret_cast<double2*>(prod)[2 * g] = p0;
+      reinterpret_cast<double2*>(prod)[2 * g + 1] = p1;
+    }
+  }
+  __syncthreads();
+  // phase B: one thread per row, products summed in column order
+  double acc = 0.0;
+  if (active) {
+    double s = 0.0;
+    for (int k = pb; k < pe; ++k) s += prod[k];
+    double res;
+    if (MODE == M_MUL) {
+      res = s;
+      a.out[row] = res;
+    } else if (MODE == M_RESID) {
+      res = e_in0 - s;
+      a.out[row] = res;
+    } else if (MODE == M_JACOBI) {
+      res = e_in1 + e_w * (e_in0 - s);
+      a.out[row] = res;
+    } else if (MODE == M_ADD) {
+      res = e_in0 + s;
+      a.out[row] = res;
+    } else if (MODE == M_RESTRICT) {
+      res = s;
+      a.out[row] = res;
+      if (a.out2) a.out2[row] = e_w * s;
+    } else {  // M_CHEB
+      const double d = a.c1 * e_aux + a.c2 * (e_w * (e_in0 - s));
+      a.out2[row] = d;
+      res = e_in1 + d;
+      a.out[row] = res;
+    }
+    if (DOT) acc = e_dot * res;
+  }
+  if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+}
+
+// ---------------------------------------------------------------------------------------------
 // halo pack: owner -> ghost (consistent!).  Stores into the neighbours' staging, then flags.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_halo_pack(const double* __restrict__ v, const int32_t* __restrict__ send_idx,

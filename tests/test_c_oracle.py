@@ -1,0 +1,34 @@
+"""The C/OpenMP oracle (oracle/pamg_oracle.c, the CPU baseline that is timed in bench.py) against
+the normative Python oracle: V-cycle <= 1e-12, identical PCG iteration counts."""
+import numpy as np
+import pytest
+
+import amg_oracle as O
+import c_oracle
+from util import det_vector, oracle_problem, own_of, own_parts, rel_err
+
+
+@pytest.mark.parametrize("dims,pp,oopts", [
+    ((200, 200), (2, 2), {}),
+    ((20, 20, 20), (2, 2, 2), {}),
+    ((33, 31, 17), (3, 2, 1), {"nu_pre": 2, "nu_post": 2}),
+    ((28, 28, 28), (1, 1, 1), {"smoother": "l1jacobi"}),
+    ((7, 5), (1, 1), {}),
+])
+def test_c_oracle_matches_python_oracle(dims, pp, oopts):
+    A, owner, h = oracle_problem(dims, pp, tuple(sorted(oopts.items())))
+    co = c_oracle.COracle.from_oracle_hierarchy(h)
+    lev = h["levels"][0]
+    n = A.shape[0]
+    b = det_vector(n, 7)
+    z_ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(co.vcycle(own_parts(lev, b)), z_ref) <= 1e-12
+    for rhs in (A @ np.ones(n) + det_vector(n, 81), b):
+        xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, rhs))
+        x, it, hist = co.pcg(own_parts(lev, rhs))
+        assert it == it_ref
+        assert np.allclose(hist, hist_ref, rtol=1e-8)
+        assert rel_err(x, own_of(lev, xs)) <= 1e-10
+    x, it, hist = co.pcg(own_parts(lev, b), precond=False, maxiter=400)
+    xs, it_ref, _ = O.pcg(h, O.pvector_from_global(lev, b), precond=False, maxiter=400)
+    assert it == it_ref

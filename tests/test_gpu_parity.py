@@ -38,12 +38,44 @@ def test_spmv_every_level(dims, pp):
 
 @pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
 def test_spmv_all_lane_widths(lanes):
-    A, h, c = make((20, 20, 20), (2, 1, 1), None, lanes_per_row=lanes)
+    A, h, c = make((20, 20, 20), (2, 1, 1), None, lanes_per_row=lanes, spmv_format=L.FORMAT_CSR)
     lev = h["levels"][0]
     x = det_vector(A.shape[0], 3)
     ref = own_of(lev, O.spmv(lev, O.pvector_from_global(lev, x)))
     assert rel_err(c.spmv(0, own_parts(lev, x)), ref) <= TOL_KERNEL
-    assert c.stats().lanes[0] == lanes
+    assert c.stats().lanes[0] == lanes and c.stats().format[0] == L.FORMAT_CSR
+
+
+@pytest.mark.parametrize("fmt", ["csr", "stream"])
+def test_both_kernel_families_vcycle_and_pcg(fmt):
+    """AUTO picks the CSR-stream kernels; the sub-warp CSR family must give the same answers."""
+    f = L.FORMAT_CSR if fmt == "csr" else L.FORMAT_STREAM
+    A, h, c = make((33, 31, 17), (3, 2, 1), None, spmv_format=f)
+    assert c.stats().format[0] == f
+    lev = h["levels"][0]
+    b = det_vector(A.shape[0], 17)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, b))
+    x, it, hist, ok = c.pcg(own_parts(lev, b))
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
+
+
+def test_stream_spmv_is_bit_identical_to_sequential_row_sums():
+    """The stream kernel rounds each product before adding them in column order, exactly like the
+    oracle's C restatement (`s += a_ij * x_j`, no FMA): y must match bit for bit on one part."""
+    import scipy.sparse as sp
+    A, h, c = make((28, 28, 28), (1, 1, 1))
+    x = det_vector(A.shape[0], 23)
+    y = c.spmv(0, [x])[0]
+    ref = np.zeros_like(x)
+    Ac = A.tocsr()
+    prod = Ac.data * x[Ac.indices]
+    for k in range(7):  # column-ordered sequential sum, vectorised over rows
+        idx = Ac.indptr[:-1] + k
+        ok = idx < Ac.indptr[1:]
+        ref[ok] = ref[ok] + prod[idx[ok]]
+    assert np.array_equal(y, ref)
 
 
 @pytest.mark.parametrize("dims,pp", PROBLEMS[:3])
