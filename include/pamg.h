@@ -122,6 +122,9 @@ int pamg_host_matvec_global(pamg_ctx* c, const double* x, double* y);
 int pamg_global_size(pamg_ctx* c, int64_t* n, int64_t* nnz);
 
 /* ---- AMG setup on the host (PartitionedSolvers `setup(amg(...), x, A, b)`) ------------- */
+/* OpenMP threads for the host-side setup (launchers such as torchrun export OMP_NUM_THREADS=1);
+ * n <= 0 restores the hardware default.  Process-wide. */
+void pamg_set_num_threads(int32_t n);
 int pamg_setup(pamg_ctx* c, const pamg_options* o);
 /* external hierarchy (built by the caller, e.g. PartitionedSolvers itself), level by level,
  * part by part, in the split format; any block pointer triple may be NULL when empty */

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "pamg_uniform_partition": [C.c_int32, _i64p, _i32p, _i32p],
     "pamg_host_matvec_global": [_ctx, _f64p, _f64p],
     "pamg_global_size": [_ctx, _i64p, _i64p],
+    "pamg_set_num_threads": [C.c_int32],
     "pamg_setup": [_ctx, _P(Options)],
     "pamg_hierarchy_begin": [_ctx, C.c_int32, _P(Options)],
     "pamg_level_upload": [_ctx, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _i64p, _i64p, _i32p, C.c_int64, C.c_int64,
@@ -101,7 +102,7 @@ PROTOTYPES = {
     "pamg_time_kernel": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(C.c_float)],
     "pamg_get_stats": [_ctx, _P(Stats)],
 }
-_RESTYPE = {"pamg_default_options": None, "pamg_destroy": None, "pamg_last_error": C.c_char_p,
+_RESTYPE = {"pamg_set_num_threads": None, "pamg_default_options": None, "pamg_destroy": None, "pamg_last_error": C.c_char_p,
             "pamg_comm_handle_bytes": C.c_int32}
 
 _lib = None
@@ -122,6 +123,11 @@ def load():
         fn.restype = _RESTYPE.get(name, C.c_int)
     _lib = lib
     return lib
+
+
+def set_num_threads(n):
+    """OpenMP threads of the host-side setup (torchrun exports OMP_NUM_THREADS=1)."""
+    load().pamg_set_num_threads(int(n))
 
 
 def _ptr(a, ctype):

@@ -1,4 +1,6 @@
 // capi.cpp — the C ABI of include/pamg.h: argument checking, exception -> status translation.
+#include <omp.h>
+
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -277,6 +279,8 @@ int pamg_global_size(pamg_ctx* c, int64_t* n, int64_t* nnz) {
     return PAMG_OK;
   });
 }
+
+void pamg_set_num_threads(int32_t n) { omp_set_num_threads(n > 0 ? n : omp_get_num_procs()); }
 
 int pamg_setup(pamg_ctx* c, const pamg_options* o) {
   return guard(c, [&] {
