@@ -41,9 +41,11 @@ typedef enum {
 enum { PAMG_SMOOTHER_JACOBI = 0, PAMG_SMOOTHER_L1JACOBI = 1, PAMG_SMOOTHER_CHEBYSHEV = 2 };
 /* kernel family for the own-own blocks: CSR = sub-warp "vector per row" (1..32 lanes chosen from the
  * mean nnz/row; 32 = warp per row); STREAM = CSR-stream (block-cooperative 128-bit coalesced loads of
- * the contiguous val/col ranges, products staged in shared memory).  AUTO picks STREAM whenever every
- * row fits the product buffer, else CSR.  The storage is plain CSR for both. */
-enum { PAMG_FORMAT_AUTO = 0, PAMG_FORMAT_CSR = 1, PAMG_FORMAT_STREAM = 2 };
+ * the contiguous val/col ranges, products staged in shared memory); the storage is plain CSR for both.
+ * SELL = SELL-C-sigma (C = 32 x sell_rows_per_thread rows per slice, column-major slices, rows sorted by
+ * length inside windows of sell_sigma rows), one thread per row, no row pointers.  AUTO decides per
+ * operator from the nnz/row distribution (padding of the SELL layout; row length vs. the STREAM buffer). */
+enum { PAMG_FORMAT_AUTO = 0, PAMG_FORMAT_CSR = 1, PAMG_FORMAT_STREAM = 2, PAMG_FORMAT_SELL = 3 };
 /* blocks of the split (own/ghost) storage of a level, PSparseMatrix own_own_values /
  * own_ghost_values (SURVEY.md App. A "PSparseMatrix") */
 enum { PAMG_A_OO = 0, PAMG_A_OG = 1, PAMG_P_OO = 2, PAMG_P_OG = 3, PAMG_R_OO = 4, PAMG_R_OG = 5 };
@@ -65,6 +67,8 @@ typedef struct {
   int32_t use_graph;      /* 1: replay the V-cycle / PCG iteration as CUDA graphs */
   int32_t lanes_per_row;  /* 0: auto (from mean nnz/row); else 1,2,4,8,16,32 for CSR */
   int32_t tail_rows;      /* levels whose global rows <= this run inside one fused tail kernel (0: off) */
+  int32_t sell_sigma;     /* SELL sorting window in rows; 0: auto (1 = no sorting when the padding is small) */
+  int32_t sell_rows_per_thread; /* 1 or 2 (C = 32 or 64; 2 => 128-bit value loads); 0: auto */
 } pamg_options;
 
 typedef struct {
@@ -88,6 +92,9 @@ typedef struct {
   int32_t n_levels;
   int32_t format[16];     /* PAMG_FORMAT_* chosen per level for A */
   int32_t lanes[16];      /* lanes per row chosen per level for A (CSR) */
+  int32_t format_p[16];   /* PAMG_FORMAT_* chosen per level for P and R (part 0 of this process) */
+  int32_t format_r[16];
+  double sell_fill[16];   /* stored entries / nnz of A's SELL layout (1.0 when A is not SELL) */
 } pamg_stats;
 
 void pamg_default_options(pamg_options* o);
@@ -161,6 +168,9 @@ int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double
  * handle blobs (torch.distributed / MPI.Allgather), nothing else crosses processes on the host. */
 int pamg_device_init(pamg_ctx* c, int32_t nlocal, const int32_t* local_parts,
                      const int32_t* device_ids);
+/* change the kernel-side knobs (spmv_format, lanes_per_row, use_graph, sell_*) of an existing hierarchy;
+ * takes effect at the next pamg_device_init.  Numerical options are ignored. */
+int pamg_set_kernel_options(pamg_ctx* c, const pamg_options* o);
 int32_t pamg_comm_handle_bytes(void);
 int pamg_comm_export(pamg_ctx* c, int32_t local_part, void* blob);
 int pamg_comm_import(pamg_ctx* c, int32_t remote_part, const void* blob);

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libpamg.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOGPU, ERR_COMM, ERR_NOTCONV, ERR_ALLOC = 0, -1, -2, -3, -4, -5, -6
 SMOOTHER_JACOBI, SMOOTHER_L1JACOBI, SMOOTHER_CHEBYSHEV = 0, 1, 2
-FORMAT_AUTO, FORMAT_CSR, FORMAT_STREAM = 0, 1, 2
+FORMAT_AUTO, FORMAT_CSR, FORMAT_STREAM, FORMAT_SELL = 0, 1, 2, 3
 A_OO, A_OG, P_OO, P_OG, R_OO, R_OG = range(6)
 BLOCK_NAMES = ("A_oo", "A_og", "P_oo", "P_og", "R_oo", "R_og")
 
@@ -29,7 +29,7 @@ class Options(C.Structure):
         ("max_levels", C.c_int32), ("smoother", C.c_int32), ("omega_jacobi", C.c_double),
         ("nu_pre", C.c_int32), ("nu_post", C.c_int32), ("cheb_degree", C.c_int32),
         ("cheb_lo_frac", C.c_double), ("cheb_hi_frac", C.c_double), ("spmv_format", C.c_int32),
-        ("use_graph", C.c_int32), ("lanes_per_row", C.c_int32), ("tail_rows", C.c_int32),
+        ("use_graph", C.c_int32), ("lanes_per_row", C.c_int32), ("tail_rows", C.c_int32), ("sell_sigma", C.c_int32), ("sell_rows_per_thread", C.c_int32),
     ]
 
 
@@ -46,6 +46,7 @@ class Stats(C.Structure):
         ("iters", C.c_int32), ("converged", C.c_int32), ("r0_norm", C.c_double), ("r_norm", C.c_double),
         ("solve_ms", C.c_double), ("vcycle_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("n_levels", C.c_int32), ("format", C.c_int32 * 16), ("lanes", C.c_int32 * 16),
+        ("format_p", C.c_int32 * 16), ("format_r", C.c_int32 * 16), ("sell_fill", C.c_double * 16),
     ]
 
 
@@ -82,6 +83,7 @@ PROTOTYPES = {
     "pamg_get_halo_plan": [_ctx, C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p],
     "pamg_get_coarse_inverse": [_ctx, _i64p, _f64p],
     "pamg_get_diag": [_ctx, C.c_int32, C.c_int32, _f64p, _f64p],
+    "pamg_set_kernel_options": [_ctx, _P(Options)],
     "pamg_device_init": [_ctx, C.c_int32, _i32p, _i32p],
     "pamg_comm_handle_bytes": [],
     "pamg_comm_export": [_ctx, C.c_int32, C.c_void_p],
@@ -315,6 +317,11 @@ class Context:
         dv = _as([0] * len(lp) if device_ids is None else device_ids, np.int32)
         self.local_parts = [int(p) for p in lp]
         self._ck(self.lib.pamg_device_init(self._h, len(lp), _ptr(lp, C.c_int32), _ptr(dv, C.c_int32)))
+
+    def set_kernel_options(self, **kw):
+        """Change spmv_format / lanes_per_row / use_graph / sell_* for the next device_init."""
+        o = self.default_options(**kw)
+        self._ck(self.lib.pamg_set_kernel_options(self._h, C.byref(o)))
 
     def comm_export(self, part):
         buf = C.create_string_buffer(self.lib.pamg_comm_handle_bytes())

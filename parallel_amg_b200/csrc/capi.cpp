@@ -146,6 +146,8 @@ void pamg_default_options(pamg_options* o) {
   o->use_graph = 1;
   o->lanes_per_row = 0;
   o->tail_rows = 0;
+  o->sell_sigma = 0;
+  o->sell_rows_per_thread = 0;
 }
 
 int pamg_create(int32_t nparts, pamg_ctx** out) {
@@ -492,6 +494,19 @@ int pamg_device_init(pamg_ctx* c, int32_t nlocal, const int32_t* local_parts, co
     need(nlocal >= 1 && nlocal <= c->nparts && local_parts, "bad local part list");
     c->eng.reset();
     c->eng.reset(new Engine(&c->h, nlocal, local_parts, device_ids));
+    return PAMG_OK;
+  });
+}
+
+int pamg_set_kernel_options(pamg_ctx* c, const pamg_options* o) {
+  return guard(c, [&] {
+    need(o && o->struct_size == (int32_t)sizeof(pamg_options), "bad options struct");
+    need(c->h.ready, "hierarchy not set up");
+    c->h.opts.spmv_format = o->spmv_format;
+    c->h.opts.lanes_per_row = o->lanes_per_row;
+    c->h.opts.use_graph = o->use_graph;
+    c->h.opts.sell_sigma = o->sell_sigma;
+    c->h.opts.sell_rows_per_thread = o->sell_rows_per_thread;
     return PAMG_OK;
   });
 }

@@ -68,9 +68,80 @@ struct DevCsr {
   DBuf<int2> blk;
   int nblocks = 0;
   bool stream = false;
+  // SELL-C-sigma (own-own blocks only)
+  DBuf<int32_t> sl_off, sl_col, sl_perm;
+  DBuf<double> sl_val;
+  int nslices = 0, sell_rpt = 0, sell_sigma = 1;  // sell_rpt != 0 <=> the SELL kernel runs this block
+  bool sell_perm = false;
+  double sell_fill = 1.0;  // stored entries / nnz
   CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
   StreamView sview() const { return StreamView{blk.p, ptr.p, col.p, val.p, nrows, nblocks}; }
+  SellView slview() const { return SellView{sl_off.p, sl_col.p, sl_val.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
 };
+
+// host-side SELL-C-sigma conversion of one own-own block; returns stored entries / nnz
+struct SellHost {
+  std::vector<int32_t> off, col, perm;
+  std::vector<double> val;
+  bool permuted = false;
+  double fill = 1.0;
+};
+
+void sell_layout(const LocalCsr& m, int C, int sigma, SellHost& out, bool fill_arrays) {
+  const int64_t nr = m.nrows;
+  const int64_t ns = (nr + C - 1) / C;
+  out.perm.resize(nr);
+  for (int64_t i = 0; i < nr; ++i) out.perm[i] = (int32_t)i;
+  out.permuted = false;
+  if (sigma > 1) {
+    for (int64_t w0 = 0; w0 < nr; w0 += sigma) {
+      const int64_t w1 = std::min<int64_t>(nr, w0 + sigma);
+      std::stable_sort(out.perm.begin() + w0, out.perm.begin() + w1, [&](int32_t a, int32_t b) {
+        return (m.ptr[a + 1] - m.ptr[a]) > (m.ptr[b + 1] - m.ptr[b]);
+      });
+    }
+    for (int64_t i = 0; i < nr && !out.permuted; ++i) out.permuted = out.perm[i] != (int32_t)i;
+  }
+  out.off.assign(ns + 1, 0);
+  for (int64_t sl = 0; sl < ns; ++sl) {
+    int64_t w = 0;
+    for (int64_t slot = sl * C; slot < std::min<int64_t>(nr, (sl + 1) * C); ++slot) {
+      const int32_t r = out.perm[slot];
+      w = std::max<int64_t>(w, m.ptr[r + 1] - m.ptr[r]);
+    }
+    const int64_t nxt = (int64_t)out.off[sl] + w;
+    if (nxt * C > INT32_MAX) throw std::runtime_error("SELL storage exceeds int32 entries");
+    out.off[sl + 1] = (int32_t)nxt;
+  }
+  const int64_t stored = (int64_t)out.off[ns] * C;
+  out.fill = m.nnz() ? (double)stored / (double)m.nnz() : 1.0;
+  if (!fill_arrays) return;
+  out.col.assign(stored + 4, 0);
+  out.val.assign(stored + 4, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int64_t sl = 0; sl < ns; ++sl) {
+    const int64_t w = out.off[sl + 1] - out.off[sl];
+    for (int64_t q = 0; q < C; ++q) {
+      const int64_t slot = sl * C + q;
+      if (slot >= nr) continue;  // tail rows of the last slice stay (0.0, column 0)
+      const int32_t r = out.perm[slot];
+      const int64_t b = m.ptr[r], len = m.ptr[r + 1] - b;
+      const int32_t padcol = len ? m.col[b + len - 1] : 0;
+      for (int64_t j = 0; j < w; ++j) {
+        const int64_t dst = ((int64_t)out.off[sl] + j) * C + q;
+        out.col[dst] = j < len ? m.col[b + j] : padcol;
+        out.val[dst] = j < len ? m.val[b + j] : 0.0;
+      }
+    }
+  }
+}
+
+// AUTO takes SELL-C-sigma when its padding stores at most this many entries per nonzero
+constexpr double SELL_AUTO_MAX_FILL = 1.25;
+// AUTO per operator (gpurun kernel sweep, profiles/r01_kernel_sweep.md): A -> SELL (0.29 vs 0.36 ms at 256^3);
+// R -> SELL only with enough coarse rows to fill the GPU one thread per row, else CSR-stream (few, long rows);
+// P (1-8 entries per row) -> CSR-stream, which ties SELL without needing a row permutation.
+constexpr int64_t SELL_AUTO_MIN_ROWS_A = 4096, SELL_AUTO_MIN_ROWS_R = 65536;
 
 int pick_lanes(double mean) {
   if (mean <= 1.5) return 1;
@@ -81,11 +152,15 @@ int pick_lanes(double mean) {
   return 32;
 }
 
-void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, bool want_stream) {
+// fmt: PAMG_FORMAT_* requested for this block (own-ghost blocks are always compressed-row CSR)
+void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, int fmt, const pamg_options& o, int which) {
   const int64_t nr = m.nrows;
   std::vector<int32_t> ptr;
   d.listed = compress;
   d.nnz = m.nnz();
+  d.stream = false;
+  d.nblocks = 0;
+  d.sell_rpt = 0;
   if (m.ptr.empty()) {  // absent block
     d.nrows = compress ? 0 : (int32_t)nr;
     ptr.assign((compress ? 0 : nr) + 1, 0);
@@ -93,7 +168,6 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     d.col.alloc(16);
     d.val.alloc(16);
     d.rows.alloc(0);
-    d.stream = false;
     return;
   }
   if (compress) {
@@ -112,6 +186,44 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     d.nrows = (int32_t)nr;
     d.rows.alloc(0);
   }
+  const double mean = d.nrows ? (double)d.nnz / d.nrows : 0.0;
+  d.lanes = lanes_override > 0 ? lanes_override : pick_lanes(mean);
+  // ---- SELL-C-sigma ----
+  bool auto_sell = false;
+  if (fmt == PAMG_FORMAT_AUTO) {
+    if (which == PAMG_A_OO) auto_sell = nr >= SELL_AUTO_MIN_ROWS_A;
+    if (which == PAMG_R_OO) auto_sell = nr >= SELL_AUTO_MIN_ROWS_R;
+  }
+  if (!compress && nr > 0 && (fmt == PAMG_FORMAT_SELL || auto_sell)) {
+    const int rpt = (o.sell_rows_per_thread == 1 || o.sell_rows_per_thread == 2) ? o.sell_rows_per_thread : 2;
+    const int C = 32 * rpt;
+    SellHost sh;
+    int sigma = o.sell_sigma > 0 ? o.sell_sigma : 1;
+    sell_layout(m, C, sigma, sh, false);
+    if (o.sell_sigma <= 0 && sh.fill > 1.05) {  // auto sigma: sort inside windows only when it pays
+      SellHost s2;
+      sell_layout(m, C, 64 * C, s2, false);
+      if (s2.fill < sh.fill - 0.02) sigma = 64 * C;
+      sh.fill = std::min(sh.fill, s2.fill);
+    }
+    const bool take = fmt == PAMG_FORMAT_SELL || sh.fill <= SELL_AUTO_MAX_FILL;
+    if (take) {
+      sell_layout(m, C, sigma, sh, true);
+      d.sl_off.upload(sh.off);
+      d.sl_col.upload(sh.col);
+      d.sl_val.upload(sh.val);
+      d.sell_perm = sh.permuted;
+      if (sh.permuted) d.sl_perm.upload(sh.perm);
+      d.nslices = (int)sh.off.size() - 1;
+      d.sell_rpt = rpt;
+      d.sell_sigma = sigma;
+      d.sell_fill = sh.fill;
+      d.ptr.alloc(1);
+      d.col.alloc(16);
+      d.val.alloc(16);
+      return;
+    }
+  }
   d.ptr.upload(ptr);
   {  // pad to a multiple of 4 entries (+8) with zeros: the stream kernel reads whole 128-bit groups
     const size_t padded = (m.col.size() + 3) / 4 * 4 + 8;
@@ -122,11 +234,7 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     d.col.upload(col);
     d.val.upload(val);
   }
-  const double mean = d.nrows ? (double)d.nnz / d.nrows : 0.0;
-  d.lanes = lanes_override > 0 ? lanes_override : pick_lanes(mean);
-  d.stream = false;
-  d.nblocks = 0;
-  if (want_stream && !compress && nr > 0) {
+  if (!compress && nr > 0 && fmt != PAMG_FORMAT_CSR) {
     // greedy row blocks: <= S_ROWS rows and <= S_CAP - 3 entries (so the 4-aligned window fits)
     std::vector<int2> blk;
     int64_t r = 0;
@@ -262,6 +370,10 @@ struct Engine::Impl {
     int64_t g = (work_items + items_per_block - 1) / items_per_block;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, MAX_GRID));
   }
+  // kernels with a fused reduction: one fence + ticket per CTA, so keep the CTA count small
+  int grid_red(int64_t work_items) const {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((work_items + BLOCK - 1) / BLOCK, RED_GRID));
+  }
   void note_launch() {
     if (counting) ++launches;
   }
@@ -369,6 +481,32 @@ void launch_stream(int mode, bool dot, int grid, cudaStream_t s, StreamView A, c
 #undef PAMG_S
 }
 
+template <int RPT>
+void launch_sell_rpt(int mode, bool dot, int grid, cudaStream_t s, SellView A, const double* x, const EpiArgs& a, DevState* st,
+                     double* partials, const RedCtx& rc, int publish, int slot) {
+#define PAMG_E(MD, DT)                                                                         \
+  k_spmv_sell<RPT, MD, DT><<<grid, BLOCK, 0, s>>>(A, x, a, st, partials, rc, publish, slot); \
+  break;
+  if (dot) {
+    switch (mode) {
+      case M_MUL: PAMG_E(M_MUL, true)
+      case M_JACOBI: PAMG_E(M_JACOBI, true)
+      default: throw std::runtime_error("fused dot only on MUL/JACOBI");
+    }
+  } else {
+    switch (mode) {
+      case M_MUL: PAMG_E(M_MUL, false)
+      case M_RESID: PAMG_E(M_RESID, false)
+      case M_JACOBI: PAMG_E(M_JACOBI, false)
+      case M_ADD: PAMG_E(M_ADD, false)
+      case M_RESTRICT: PAMG_E(M_RESTRICT, false)
+      case M_CHEB: PAMG_E(M_CHEB, false)
+      default: throw std::runtime_error("bad mode");
+    }
+  }
+#undef PAMG_E
+}
+
 }  // namespace
 
 // One SpMV-family operation over all local parts:  [pack halo of xin] ; main (own-own) ; [own-ghost correction].
@@ -411,9 +549,23 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     const DevCsr& m = ld.blk[op.which];
     const bool og_follows = need && hl.n_recv_nbrs > 0;
     I.set_dev(pd);
+    if (m.sell_rpt) {
+      const int wpb = BLOCK / 32;
+      int grid = (m.nslices + wpb - 1) / wpb;
+      if (op.dot) grid = std::min(grid, RED_GRID);
+      grid = std::max(grid, 1);
+      if (m.sell_rpt == 2)
+        launch_sell_rpt<2>(op.mode, op.dot, grid, pd.stream, m.slview(), xin[i], epi[i], pd.st.p, pd.partials.p, pd.rc,
+                           og_follows ? 0 : 1, op.slot);
+      else
+        launch_sell_rpt<1>(op.mode, op.dot, grid, pd.stream, m.slview(), xin[i], epi[i], pd.st.p, pd.partials.p, pd.rc,
+                           og_follows ? 0 : 1, op.slot);
+      I.note_launch();
+      continue;
+    }
     if (m.stream) {
-      launch_stream(op.mode, op.dot, m.nblocks, pd.stream, m.sview(), xin[i], epi[i], pd.st.p, pd.partials.p, pd.rc,
-                    og_follows ? 0 : 1, op.slot);
+      launch_stream(op.mode, op.dot, op.dot ? std::min(m.nblocks, RED_GRID) : m.nblocks, pd.stream, m.sview(), xin[i], epi[i],
+                    pd.st.p, pd.partials.p, pd.rc, og_follows ? 0 : 1, op.slot);
       I.note_launch();
       continue;
     }
@@ -517,7 +669,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         const bool og = (b & 1);
         int lanes = 0;
         if (!og && b == PAMG_A_OO && o.lanes_per_row > 0) lanes = o.lanes_per_row;
-        build_csr(pl.blk[b], og, ld.blk[b], og ? 4 : lanes, !og && o.spmv_format != PAMG_FORMAT_CSR);
+        build_csr(pl.blk[b], og, ld.blk[b], og ? 4 : lanes, og ? PAMG_FORMAT_CSR : o.spmv_format, o, b);
         max_blocks = std::max(max_blocks, ld.blk[b].nblocks);
       }
       // smoother weights
@@ -986,7 +1138,7 @@ void Engine::enqueue_dot_rz() {
     PartDev& pd = *up;
     LevelDev& l0 = *pd.lev[0];
     I.set_dev(pd);
-    k_dot<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p, pd.rc,
+    k_dot<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p, pd.rc,
                                                                    1, 1);
     I.note_launch();
   }
@@ -1012,7 +1164,7 @@ void Engine::enqueue_pcg_iteration(bool precond) {
       PartDev& pd = *up;
       LevelDev& l0 = *pd.lev[0];
       I.set_dev(pd);
-      k_copy_dot<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p,
+      k_copy_dot<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p,
                                                                           pd.rc);
       I.note_launch();
     }
@@ -1040,7 +1192,7 @@ void Engine::enqueue_pcg_iteration(bool precond) {
     PartDev& pd = *up;
     LevelDev& l0 = *pd.lev[0];
     I.set_dev(pd);
-    k_update_xr<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.xsol.p, l0.b.p, pd.p.p, pd.q.p, l0.xstart,
+    k_update_xr<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.xsol.p, l0.b.p, pd.p.p, pd.q.p, l0.xstart,
                                                                          zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
                                                                          pd.partials.p, pd.rc);
     I.note_launch();
@@ -1206,7 +1358,7 @@ double Engine::dot(int level, const double* const* u, const double* const* v) {
     PartDev& pd = *up;
     LevelDev& ld = *pd.lev[level];
     I.set_dev(pd);
-    k_dot<<<I.grid_for(ld.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
+    k_dot<<<I.grid_red(ld.n_own), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
     I.note_launch();
   }
   double out[RED_W] = {0, 0, 0, 0};
@@ -1377,7 +1529,7 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
     LevelDev& l0 = *pd.lev[0];
     I.set_dev(pd);
     CK(cudaEventRecord(pd.ev0, pd.stream));
-    k_pcg_init<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.bsave.p, pd.xsol.p, l0.b.p, pd.p.p, l0.xstart,
+    k_pcg_init<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.bsave.p, pd.xsol.p, l0.b.p, pd.p.p, l0.xstart,
                                                                         zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
                                                                         pd.partials.p, pd.rc, rtol, maxiter);
     I.note_launch();
@@ -1500,7 +1652,7 @@ void Engine::time_kernel(int kind, int level, int reps, bool flush_l2, float* ms
         PartDev& pd = *up;
         LevelDev& ld = *pd.lev[level];
         I.set_dev(pd);
-        k_dot<<<I.grid_for(ld.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
+        k_dot<<<I.grid_red(ld.n_own), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
       }
     } else if (kind == 5) {
       const bool use_graph = I.h->opts.use_graph != 0;
@@ -1526,9 +1678,14 @@ void Engine::get_stats(pamg_stats* s) {
   Impl& I = *impl;
   *s = I.stats;
   s->n_levels = I.L;
+  auto fmt_of = [](const DevCsr& m) { return m.sell_rpt ? PAMG_FORMAT_SELL : m.stream ? PAMG_FORMAT_STREAM : PAMG_FORMAT_CSR; };
   for (int l = 0; l < 16; ++l) {
-    s->format[l] = (l < I.L && !I.parts.empty()) ? (I.P(0).lev[l]->blk[PAMG_A_OO].stream ? PAMG_FORMAT_STREAM : PAMG_FORMAT_CSR) : 0;
-    s->lanes[l] = (l < I.L && !I.parts.empty()) ? I.P(0).lev[l]->blk[PAMG_A_OO].lanes : 0;
+    const bool have = l < I.L && !I.parts.empty();
+    s->format[l] = have ? fmt_of(I.P(0).lev[l]->blk[PAMG_A_OO]) : 0;
+    s->format_p[l] = have && l + 1 < I.L ? fmt_of(I.P(0).lev[l]->blk[PAMG_P_OO]) : 0;
+    s->format_r[l] = have && l + 1 < I.L ? fmt_of(I.P(0).lev[l]->blk[PAMG_R_OO]) : 0;
+    s->lanes[l] = have ? I.P(0).lev[l]->blk[PAMG_A_OO].lanes : 0;
+    s->sell_fill[l] = have ? I.P(0).lev[l]->blk[PAMG_A_OO].sell_fill : 1.0;
   }
 }
 

@@ -109,6 +109,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ldg_stream(const int32_t* p) { return __ldcs(p); }
 
+// Load that the compiler may not sink to its use: the epilogue operands of a row are requested BEFORE
+// the row's entries are streamed, so their latency overlaps the main loop (without this nvcc moves the
+// loads below the loop and the SELL Jacobi sweep runs 2x slower than the plain SpMV; gpurun sweep r01).
+__device__ __forceinline__ double ld_early(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t e, DevState* st) {
   if ((int32_t)(ld_acquire_sys(flag) - e) >= 0) return;
   if (*(volatile int32_t*)&st->error) return;  // a wait already timed out: fail fast, the host reports it
@@ -329,9 +338,11 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
 // phase A.  Products are rounded before they are added (no FMA across the smem round trip), so a
 // row sum is bit-identical to the oracle's sequential `s += a_ij * x_j`.
 // ---------------------------------------------------------------------------------------------
-constexpr int S_CAP = 3072;   // entries per CTA (24 KB of fp64 products)
-constexpr int S_ROWS = BLOCK; // at most one row per thread in phase B
+constexpr int S_CAP = 3072;        // entries per row block (24 KB of fp64 products)
+constexpr int S_CHUNKS = 4;        // phase B handles up to S_CHUNKS rows per thread
+constexpr int S_ROWS = S_CHUNKS * BLOCK;  // rows per row block
 constexpr int S_STEPS = (S_CAP + 4 * BLOCK - 1) / (4 * BLOCK);
+constexpr int RED_GRID = 148 * 8;  // CTAs of a kernel with a fused reduction (one fence + ticket per CTA)
 
 struct StreamView {
   const int2* blk;     // [nblocks + 1] {first row, first entry} of each row block
@@ -341,89 +352,219 @@ struct StreamView {
   int32_t nrows, nblocks;
 };
 
+template <int MODE>
+__device__ __forceinline__ double stream_epilogue(const EpiArgs& a, int row, double s, double e_in0, double e_in1, double e_w,
+                                                  double e_aux) {
+  double res;
+  if (MODE == M_MUL) {
+    res = s;
+    a.out[row] = res;
+  } else if (MODE == M_RESID) {
+    res = e_in0 - s;
+    a.out[row] = res;
+  } else if (MODE == M_JACOBI) {
+    res = e_in1 + e_w * (e_in0 - s);
+    a.out[row] = res;
+  } else if (MODE == M_ADD) {
+    res = e_in0 + s;
+    a.out[row] = res;
+  } else if (MODE == M_RESTRICT) {
+    res = s;
+    a.out[row] = res;
+    if (a.out2) a.out2[row] = e_w * s;
+  } else {  // M_CHEB
+    const double d = a.c1 * e_aux + a.c2 * (e_w * (e_in0 - s));
+    a.out2[row] = d;
+    res = e_in1 + d;
+    a.out[row] = res;
+  }
+  return res;
+}
+
+// The grid is the number of row blocks (one block per CTA, hardware-scheduled) except for the
+// variants with a fused dot product, which run RED_GRID CTAs that stride over the row blocks: a
+// gpu-scope fence per CTA (needed by the last-block reduction) invalidates the SM's L1, so it must
+// not happen once per row block (ncu r01: +45 % time with 65536 fencing CTAs).
 template <int MODE, bool DOT>
-__global__ void __launch_bounds__(BLOCK) k_spmv_stream(StreamView A, const double* __restrict__ x, EpiArgs a, DevState* st,
+__global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const double* __restrict__ x, EpiArgs a, DevState* st,
                                                         double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
   __shared__ double prod[S_STEPS * 4 * BLOCK];
   const int t = threadIdx.x;
-  const int2 b0 = A.blk[blockIdx.x], b1 = A.blk[blockIdx.x + 1];
-  const int r0 = b0.x, nr = b1.x - b0.x;
-  const int ea = b0.y & ~3;              // 4-entry aligned start: 16 B (col) / 32 B (val) aligned
-  const int n4 = (b1.y - ea + 3) >> 2;   // 4-entry groups to stream (<= S_STEPS * BLOCK by construction)
-  const int row = r0 + t;
-  const bool active = t < nr;
-  // prefetch row extents and epilogue operands; their latency overlaps phase A
-  int pb = 0, pe = 0;
-  double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0, e_dot = 0.0;
-  if (active) {
-    pb = A.ptr[row] - ea;
-    pe = A.ptr[row + 1] - ea;
-    if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
-    if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
-    if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
-    if (MODE == M_CHEB && a.aux) e_aux = a.aux[row];
-    if (DOT) e_dot = a.dotv[row];
-  }
-  // phase A: stream entries [ea, ea + 4 n4).  Entries outside the block's own range belong to the
-  // neighbouring blocks (or the zero padding): valid data, their products are simply never read.
-  const int4* __restrict__ col4 = reinterpret_cast<const int4*>(A.col + ea);
-  const double2* __restrict__ val2 = reinterpret_cast<const double2*>(A.val + ea);
-  int4 c[S_STEPS];
-  double2 v0[S_STEPS], v1[S_STEPS];
-#pragma unroll
-  for (int j = 0; j < S_STEPS; ++j) {
-    const int g = t + j * BLOCK;
-    if (g < n4) {
-      c[j] = __ldcs(col4 + g);
-      v0[j] = __ldcs(val2 + 2 * g);
-      v1[j] = __ldcs(val2 + 2 * g + 1);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < S_STEPS; ++j) {
-    const int g = t + j * BLOCK;
-    if (g < n4) {
-      const double x0 = x[c[j].x], x1 = x[c[j].y], x2 = x[c[j].z], x3 = x[c[j].w];
-      double2 p0, p1;
-      p0.x = v0[j].x * x0;
-      p0.y = v0[j].y * x1;
-      p1.x = v1[j].x * x2;
-      p1.y = v1[j].y * x3;
-      reinterpret_cast<double2*>(prod)[2 * g] = p0;
-      reinterpret_cast<double2*>(prod)[2 * g + 1] = p1;
-    }
-  }
-  __syncthreads();
-  // phase B: one thread per row, products summed in column order
   double acc = 0.0;
-  if (active) {
-    double s = 0.0;
-    for (int k = pb; k < pe; ++k) s += prod[k];
-    double res;
-    if (MODE == M_MUL) {
-      res = s;
-      a.out[row] = res;
-    } else if (MODE == M_RESID) {
-      res = e_in0 - s;
-      a.out[row] = res;
-    } else if (MODE == M_JACOBI) {
-      res = e_in1 + e_w * (e_in0 - s);
-      a.out[row] = res;
-    } else if (MODE == M_ADD) {
-      res = e_in0 + s;
-      a.out[row] = res;
-    } else if (MODE == M_RESTRICT) {
-      res = s;
-      a.out[row] = res;
-      if (a.out2) a.out2[row] = e_w * s;
-    } else {  // M_CHEB
-      const double d = a.c1 * e_aux + a.c2 * (e_w * (e_in0 - s));
-      a.out2[row] = d;
-      res = e_in1 + d;
-      a.out[row] = res;
+  for (int bk = blockIdx.x; bk < A.nblocks; bk += gridDim.x) {
+    const int2 b0 = A.blk[bk], b1 = A.blk[bk + 1];
+    const int r0 = b0.x, nr = b1.x - b0.x;
+    const int ea = b0.y & ~3;              // 4-entry aligned start: 16 B (col) / 32 B (val) aligned
+    const int n4 = (b1.y - ea + 3) >> 2;   // 4-entry groups to stream (<= S_STEPS * BLOCK by construction)
+    // prefetch row extents and the first chunk's epilogue operands; their latency overlaps phase A
+    int pb = 0, pe = 0;
+    double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0, e_dot = 0.0;
+    if (t < nr) {
+      const int row = r0 + t;
+      pb = A.ptr[row] - ea;
+      pe = A.ptr[row + 1] - ea;
+      if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
+      if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
+      if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
+      if (MODE == M_CHEB && a.aux) e_aux = a.aux[row];
+      if (DOT) e_dot = a.dotv[row];
     }
-    if (DOT) acc = e_dot * res;
+    // phase A: stream entries [ea, ea + 4 n4).  Entries outside the block's own range belong to the
+    // neighbouring blocks (or the zero padding): valid data, their products are simply never read.
+    const int4* __restrict__ col4 = reinterpret_cast<const int4*>(A.col + ea);
+    const double2* __restrict__ val2 = reinterpret_cast<const double2*>(A.val + ea);
+    int4 c[S_STEPS];
+    double2 v0[S_STEPS], v1[S_STEPS];
+#pragma unroll
+    for (int j = 0; j < S_STEPS; ++j) {
+      const int g = t + j * BLOCK;
+      if (g < n4) {
+        c[j] = __ldcs(col4 + g);
+        v0[j] = __ldcs(val2 + 2 * g);
+        v1[j] = __ldcs(val2 + 2 * g + 1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < S_STEPS; ++j) {
+      const int g = t + j * BLOCK;
+      if (g < n4) {
+        const double x0 = x[c[j].x], x1 = x[c[j].y], x2 = x[c[j].z], x3 = x[c[j].w];
+        double2 p0, p1;
+        p0.x = v0[j].x * x0;
+        p0.y = v0[j].y * x1;
+        p1.x = v1[j].x * x2;
+        p1.y = v1[j].y * x3;
+        reinterpret_cast<double2*>(prod)[2 * g] = p0;
+        reinterpret_cast<double2*>(prod)[2 * g + 1] = p1;
+      }
+    }
+    __syncthreads();
+    // phase B: thread t owns rows t, t + BLOCK, ...; products summed in column order
+#pragma unroll
+    for (int q = 0; q < S_CHUNKS; ++q) {
+      const int rr = t + q * BLOCK;
+      if (rr < nr) {
+        const int row = r0 + rr;
+        if (q > 0) {  // extents / operands of the later chunks (short-row matrices only) are fetched here
+          pb = A.ptr[row] - ea;
+          pe = A.ptr[row + 1] - ea;
+          if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
+          if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
+          if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
+          if (MODE == M_CHEB && a.aux) e_aux = a.aux[row];
+          if (DOT) e_dot = a.dotv[row];
+        }
+        double s = 0.0;
+        for (int k = pb; k < pe; ++k) s += prod[k];
+        const double res = stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
+        if (DOT) acc += e_dot * res;
+      }
+    }
+    if (bk + (int)gridDim.x < A.nblocks) __syncthreads();  // prod is reused by the next row block
+  }
+  if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SELL-C-sigma SpMV family.  C = 32 * RPT rows per slice = one warp; lane l owns RPT adjacent rows
+// of the slice.  Slice storage is column-major: entry j of the slice's rows is one contiguous,
+// aligned run of C values (and C column ids), so a warp's load of entry j is one fully coalesced
+// 256 B * RPT (values) / 128 B * RPT (column ids) transaction -- 128-bit per thread for the values
+// when RPT = 2 -- and there is no row pointer, no shared memory and no cross-lane reduction.
+// Rows are sorted by length (descending, stable) inside windows of sigma rows before slicing, which
+// bounds the padding for the variable-length rows of P and R; `perm` maps a slot back to its row.
+// Padding entries are (value 0.0, column = a valid column of the row): they add +0.0.
+// A row is summed sequentially in column order with the product rounded before the addition
+// (__dmul_rn / __dadd_rn: no FMA contraction), i.e. bit-identically to the oracle's CSR loop.
+// ---------------------------------------------------------------------------------------------
+struct SellView {
+  const int32_t* slice_off;  // [nslices + 1] first entry-row of each slice, in units of C entries
+  const int32_t* col;        // [slice_off[nslices] * C]
+  const double* val;
+  const int32_t* perm;       // slot -> row, or nullptr (identity)
+  int32_t nrows, nslices;
+};
+
+template <int RPT>
+struct SellVec;
+template <>
+struct SellVec<1> {
+  using V = double;
+  using I = int32_t;
+};
+template <>
+struct SellVec<2> {
+  using V = double2;
+  using I = int2;
+};
+__device__ __forceinline__ double sv_get(const double& v, int) { return v; }
+__device__ __forceinline__ double sv_get(const double2& v, int k) { return k ? v.y : v.x; }
+__device__ __forceinline__ int sv_get(const int32_t& v, int) { return v; }
+__device__ __forceinline__ int sv_get(const int2& v, int k) { return k ? v.y : v.x; }
+
+template <int RPT, int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView A, const double* __restrict__ x, EpiArgs a, DevState* st,
+                                                      double* partials, RedCtx rc, int publish, int red_slot) {
+  if (st->done) return;
+  using V = typename SellVec<RPT>::V;
+  using I = typename SellVec<RPT>::I;
+  constexpr int U = RPT == 1 ? 8 : 4;  // entries of a row in flight per step
+  const int lane = threadIdx.x & 31;
+  const int wpb = BLOCK / 32;
+  double acc = 0.0;
+  for (int sl = blockIdx.x * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += gridDim.x * wpb) {
+    const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
+    const int slot0 = sl * (32 * RPT) + lane * RPT;
+    int row[RPT];
+    double e_in0[RPT], e_in1[RPT], e_w[RPT], e_aux[RPT], e_dot[RPT], s[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int slot = slot0 + k;
+      row[k] = -1;
+      e_in0[k] = e_in1[k] = e_w[k] = e_aux[k] = e_dot[k] = 0.0;
+      s[k] = 0.0;
+      if (slot < A.nrows) {
+        const int r = A.perm ? A.perm[slot] : slot;
+        row[k] = r;
+        if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0[k] = ld_early(a.in0 + r);
+        if (MODE == M_JACOBI || MODE == M_CHEB) e_in1[k] = ld_early(a.in1 + r);
+        if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w[k] = ld_early(a.w + r);
+        if (MODE == M_CHEB && a.aux) e_aux[k] = ld_early(a.aux + r);
+        if (DOT) e_dot[k] = ld_early(a.dotv + r);
+      }
+    }
+    const V* __restrict__ vp = reinterpret_cast<const V*>(A.val) + (size_t)o0 * 32 + lane;
+    const I* __restrict__ cp = reinterpret_cast<const I*>(A.col) + (size_t)o0 * 32 + lane;
+    for (int j0 = 0; j0 < w; j0 += U) {
+      V v[U];
+      I c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) {
+          c[u] = __ldcs(cp + (size_t)(j0 + u) * 32);
+          v[u] = __ldcs(vp + (size_t)(j0 + u) * 32);
+        }
+      double xv[U][RPT];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) {
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) xv[u][k] = x[sv_get(c[u], k)];
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) {
+#pragma unroll
+          for (int k = 0; k < RPT; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(sv_get(v[u], k), xv[u][k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k)
+      if (row[k] >= 0) {
+        const double res = stream_epilogue<MODE>(a, row[k], s[k], e_in0[k], e_in1[k], e_w[k], e_aux[k]);
+        if (DOT) acc += e_dot[k] * res;
+      }
   }
   if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }

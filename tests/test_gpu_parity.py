@@ -46,12 +46,30 @@ def test_spmv_all_lane_widths(lanes):
     assert c.stats().lanes[0] == lanes and c.stats().format[0] == L.FORMAT_CSR
 
 
-@pytest.mark.parametrize("fmt", ["csr", "stream"])
-def test_both_kernel_families_vcycle_and_pcg(fmt):
-    """AUTO picks the CSR-stream kernels; the sub-warp CSR family must give the same answers."""
-    f = L.FORMAT_CSR if fmt == "csr" else L.FORMAT_STREAM
-    A, h, c = make((33, 31, 17), (3, 2, 1), None, spmv_format=f)
-    assert c.stats().format[0] == f
+FORMATS = {"csr": dict(spmv_format=L.FORMAT_CSR), "stream": dict(spmv_format=L.FORMAT_STREAM),
+           "sell1": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=1, sell_sigma=1),
+           "sell2": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=2),
+           "sell2-sorted": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=2, sell_sigma=256),
+           "sell1-sorted": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=1, sell_sigma=96)}
+
+
+@pytest.mark.parametrize("fmt", sorted(FORMATS))
+def test_all_kernel_families_vcycle_and_pcg(fmt):
+    """Every SpMV family (sub-warp CSR, CSR-stream, SELL-C-sigma with and without row sorting) must
+    give the same answers: per-level operators, the V-cycle and the PCG iteration count."""
+    A, h, c = make((33, 31, 17), (3, 2, 1), None, **FORMATS[fmt])
+    f = FORMATS[fmt]["spmv_format"]
+    assert c.stats().format[0] == f and c.stats().format_p[0] == f and c.stats().format_r[0] == f
+    for l in range(len(h["levels"]) - 1):
+        lev, nxt = h["levels"][l], h["levels"][l + 1]
+        gl = h["global"]["levels"][l]
+        n, nc = gl["A"].shape[0], h["global"]["levels"][l + 1]["A"].shape[0]
+        b_, x_, ec = det_vector(n, 41), det_vector(n, 42), det_vector(nc, 43)
+        assert rel_err(c.spmv(l, own_parts(lev, x_)), own_parts(lev, gl["A"] @ x_)) <= TOL_KERNEL
+        r, bc = c.residual_restrict(l, own_parts(lev, b_), own_parts(lev, x_))
+        assert rel_err(bc, own_parts(nxt, gl["R"] @ (b_ - gl["A"] @ x_))) <= 4 * TOL_KERNEL
+        got = c.prolong_correct(l, own_parts(nxt, ec), own_parts(lev, x_))
+        assert rel_err(got, own_parts(lev, x_ + gl["P"] @ ec)) <= TOL_KERNEL
     lev = h["levels"][0]
     b = det_vector(A.shape[0], 17)
     ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
@@ -61,11 +79,11 @@ def test_both_kernel_families_vcycle_and_pcg(fmt):
     assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
 
 
-def test_stream_spmv_is_bit_identical_to_sequential_row_sums():
-    """The stream kernel rounds each product before adding them in column order, exactly like the
-    oracle's C restatement (`s += a_ij * x_j`, no FMA): y must match bit for bit on one part."""
-    import scipy.sparse as sp
-    A, h, c = make((28, 28, 28), (1, 1, 1))
+@pytest.mark.parametrize("fmt", ["stream", "sell1", "sell2", "sell2-sorted"])
+def test_spmv_is_bit_identical_to_sequential_row_sums(fmt):
+    """The stream and SELL kernels round each product before adding them in column order, exactly like
+    the oracle's C restatement (`s += a_ij * x_j`, no FMA): y must match bit for bit on one part."""
+    A, h, c = make((28, 28, 28), (1, 1, 1), None, **FORMATS[fmt])
     x = det_vector(A.shape[0], 23)
     y = c.spmv(0, [x])[0]
     ref = np.zeros_like(x)
