@@ -69,6 +69,8 @@ typedef struct {
   int32_t tail_rows;      /* levels whose global rows <= this run inside one fused tail kernel (0: off) */
   int32_t sell_sigma;     /* SELL sorting window in rows; 0: auto (1 = no sorting when the padding is small) */
   int32_t sell_rows_per_thread; /* 1 or 2 (C = 32 or 64; 2 => 128-bit value loads); 0: auto */
+  int32_t fuse_halo;      /* 1: halo pack / wait / boundary rows run inside the consuming kernel whenever every local
+                             part has a GPU of its own; 0: always three launches (env PAMG_FUSE_HALO overrides) */
 } pamg_options;
 
 typedef struct {
@@ -95,6 +97,7 @@ typedef struct {
   int32_t format_p[16];   /* PAMG_FORMAT_* chosen per level for P and R (part 0 of this process) */
   int32_t format_r[16];
   double sell_fill[16];   /* stored entries / nnz of A's SELL layout (1.0 when A is not SELL) */
+  int32_t fused_halo;     /* 1 when the halo roles run inside the consuming kernels */
 } pamg_stats;
 
 void pamg_default_options(pamg_options* o);

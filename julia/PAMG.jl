@@ -22,7 +22,7 @@ struct Options            # mirrors pamg_options (include/pamg.h); filled by pam
     struct_size::Int32; eps_strength::Float64; coarse_size::Int32; max_levels::Int32
     smoother::Int32; omega_jacobi::Float64; nu_pre::Int32; nu_post::Int32; cheb_degree::Int32
     cheb_lo_frac::Float64; cheb_hi_frac::Float64; spmv_format::Int32; use_graph::Int32
-    lanes_per_row::Int32; tail_rows::Int32; sell_sigma::Int32; sell_rows_per_thread::Int32
+    lanes_per_row::Int32; tail_rows::Int32; sell_sigma::Int32; sell_rows_per_thread::Int32; fuse_halo::Int32
 end
 
 mutable struct Setup

@@ -29,7 +29,7 @@ class Options(C.Structure):
         ("max_levels", C.c_int32), ("smoother", C.c_int32), ("omega_jacobi", C.c_double),
         ("nu_pre", C.c_int32), ("nu_post", C.c_int32), ("cheb_degree", C.c_int32),
         ("cheb_lo_frac", C.c_double), ("cheb_hi_frac", C.c_double), ("spmv_format", C.c_int32),
-        ("use_graph", C.c_int32), ("lanes_per_row", C.c_int32), ("tail_rows", C.c_int32), ("sell_sigma", C.c_int32), ("sell_rows_per_thread", C.c_int32),
+        ("use_graph", C.c_int32), ("lanes_per_row", C.c_int32), ("tail_rows", C.c_int32), ("sell_sigma", C.c_int32), ("sell_rows_per_thread", C.c_int32), ("fuse_halo", C.c_int32),
     ]
 
 
@@ -46,7 +46,7 @@ class Stats(C.Structure):
         ("iters", C.c_int32), ("converged", C.c_int32), ("r0_norm", C.c_double), ("r_norm", C.c_double),
         ("solve_ms", C.c_double), ("vcycle_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("n_levels", C.c_int32), ("format", C.c_int32 * 16), ("lanes", C.c_int32 * 16),
-        ("format_p", C.c_int32 * 16), ("format_r", C.c_int32 * 16), ("sell_fill", C.c_double * 16),
+        ("format_p", C.c_int32 * 16), ("format_r", C.c_int32 * 16), ("sell_fill", C.c_double * 16), ("fused_halo", C.c_int32),
     ]
 
 

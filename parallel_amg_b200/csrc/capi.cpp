@@ -148,6 +148,7 @@ void pamg_default_options(pamg_options* o) {
   o->tail_rows = 0;
   o->sell_sigma = 0;
   o->sell_rows_per_thread = 0;
+  o->fuse_halo = 1;
 }
 
 int pamg_create(int32_t nparts, pamg_ctx** out) {
@@ -507,6 +508,7 @@ int pamg_set_kernel_options(pamg_ctx* c, const pamg_options* o) {
     c->h.opts.use_graph = o->use_graph;
     c->h.opts.sell_sigma = o->sell_sigma;
     c->h.opts.sell_rows_per_thread = o->sell_rows_per_thread;
+    c->h.opts.fuse_halo = o->fuse_halo;
     return PAMG_OK;
   });
 }

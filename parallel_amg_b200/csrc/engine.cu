@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <type_traits>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -136,12 +138,57 @@ void sell_layout(const LocalCsr& m, int C, int sigma, SellHost& out, bool fill_a
   }
 }
 
+// boundary rows of one operator (rows of the own-own block that also have own-ghost entries), stored
+// whole for the boundary role: own-column entries then ghost-column entries
+struct DevBnd {
+  DBuf<int32_t> rows, ptr, mid, col;
+  DBuf<double> val;
+  DBuf<uint8_t> skip;  // [rows of the block] 1 = boundary row
+  int n = 0, lanes = 4;
+  BndView view() const { return BndView{rows.p, ptr.p, mid.p, col.p, val.p, n, lanes}; }
+};
+
+int pick_lanes(double mean);
+
+void build_bnd(const LocalCsr& oo, const LocalCsr& og, DevBnd& d) {
+  const int64_t nr = oo.nrows;
+  std::vector<int32_t> rows, ptr{0}, mid, col;
+  std::vector<double> val;
+  std::vector<uint8_t> skip((size_t)std::max<int64_t>(nr, 1), 0);
+  if (!og.ptr.empty())
+    for (int64_t i = 0; i < nr; ++i) {
+      if (og.ptr[i + 1] == og.ptr[i]) continue;
+      rows.push_back((int32_t)i);
+      skip[i] = 1;
+      if (!oo.ptr.empty())
+        for (int64_t k = oo.ptr[i]; k < oo.ptr[i + 1]; ++k) {
+          col.push_back(oo.col[k]);
+          val.push_back(oo.val[k]);
+        }
+      mid.push_back((int32_t)col.size());
+      for (int64_t k = og.ptr[i]; k < og.ptr[i + 1]; ++k) {
+        col.push_back(og.col[k]);
+        val.push_back(og.val[k]);
+      }
+      ptr.push_back((int32_t)col.size());
+    }
+  d.n = (int)rows.size();
+  d.lanes = std::min(32, std::max(2, pick_lanes(d.n ? (double)col.size() / d.n : 0.0)));
+  d.rows.upload(rows);
+  d.ptr.upload(ptr);
+  d.mid.upload(mid);
+  d.col.upload(col);
+  d.val.upload(val);
+  d.skip.upload(skip);
+}
+
 // AUTO takes SELL-C-sigma when its padding stores at most this many entries per nonzero
 constexpr double SELL_AUTO_MAX_FILL = 1.25;
 // AUTO per operator (gpurun kernel sweep, profiles/r01_kernel_sweep.md): A -> SELL (0.29 vs 0.36 ms at 256^3);
 // R -> SELL only with enough coarse rows to fill the GPU one thread per row, else CSR-stream (few, long rows);
 // P (1-8 entries per row) -> CSR-stream, which ties SELL without needing a row permutation.
-constexpr int64_t SELL_AUTO_MIN_ROWS_A = 4096, SELL_AUTO_MIN_ROWS_R = 65536;
+// (one thread per row needs >= ~200k rows to fill 148 SMs: at 44k rows x 68 nnz the SELL sweep takes 63 us, CSR-stream 20 us)
+constexpr int64_t SELL_AUTO_MIN_ROWS_A = 200000, SELL_AUTO_MIN_ROWS_R = 65536;
 
 int pick_lanes(double mean) {
   if (mean <= 1.5) return 1;
@@ -290,7 +337,8 @@ ArenaLayout arena_layout(const Hierarchy& h, int part) {
 
 struct LevelDev {
   int64_t n_own = 0, n_ghost = 0;
-  DevCsr blk[6];
+  DevCsr blk[6];      // own-own blocks at even indices (own-ghost blocks live in `bnd`)
+  DevBnd bnd[3];      // boundary rows of A, P, R
   DBuf<double> w;     // smoother weight: w/a_ii (Jacobi), 1/l1-diag (l1), 1/(theta a_ii) (Chebyshev zero-guess step)
   DBuf<double> dinv;  // 1/a_ii (Chebyshev)
   DBuf<double> x, x2, b, t, d, d2;
@@ -343,6 +391,7 @@ struct Engine::Impl {
   std::vector<void*> ipc_opened;
   std::map<int, cudaStream_t> stream_of_device;
   bool connected = false;
+  bool fused_halo = false;  // every local part has a GPU of its own: halo roles run inside the consuming kernel
   int64_t launches = 0;
   bool counting = true;
   // exchange needed per level/operator (decided on global metadata so every part agrees)
@@ -405,50 +454,64 @@ Engine::Impl::~Impl() {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-template <int MODE, bool DOT, bool OG>
-void launch_spmv_lanes(int lanes, int grid, cudaStream_t s, CsrView A, const double* x, const EpiArgs& a, DevState* st,
-                       const HaloRecv& hr, int level, int fixed_parity, double* partials, const RedCtx& rc, int publish,
-                       int slot) {
-#define PAMG_L(LN)                                                                                                  \
-  case LN:                                                                                                          \
-    k_spmv<LN, MODE, DOT, OG><<<grid, BLOCK, 0, s>>>(A, x, a, st, hr, level, fixed_parity, partials, rc, publish, slot); \
-    break;
-  switch (lanes) {
-    PAMG_L(1)
-    PAMG_L(2)
-    PAMG_L(4)
-    PAMG_L(8)
-    PAMG_L(16)
-    PAMG_L(32)
-    default:
-      throw std::runtime_error("bad lanes_per_row");
-  }
-#undef PAMG_L
+// CTAs of `kernel` that are resident at once on the current device (148 SMs x occupancy): the grid of a
+// kernel with a fused reduction, so that it runs as exactly one wave of persistent CTAs
+int resident_ctas(const void* kernel) {
+  static std::map<std::pair<int, const void*>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto key = std::make_pair(dev, kernel);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0) != cudaSuccess) per_sm = 2;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  const int r = std::max(1, per_sm * sms);
+  cache[key] = r;
+  return r;
 }
 
-template <bool DOT, bool OG>
-void launch_spmv_mode(int mode, int lanes, int grid, cudaStream_t s, CsrView A, const double* x, const EpiArgs& a,
-                      DevState* st, const HaloRecv& hr, int level, int fixed_parity, double* partials, const RedCtx& rc,
-                      int publish, int slot) {
-#define PAMG_M(MD)                                                                                           \
-  case MD:                                                                                                   \
-    launch_spmv_lanes<MD, DOT, OG>(lanes, grid, s, A, x, a, st, hr, level, fixed_parity, partials, rc, publish, slot); \
+struct LaunchArgs {  // what every SpMV-family launch shares
+  int grid;            // boundary launch: the grid; main launches: natural number of main CTAs
+  bool bounded;        // main launches: cap the main CTAs at one resident wave (fused reductions)
+  cudaStream_t s;
+  const double* x;
+  EpiArgs a;
+  DevState* st;
+  FusedHalo fh;
+  double* partials;
+  RedCtx rc;
+  int publish, slot;
+};
+
+int main_grid(const LaunchArgs& L, const void* kernel) {
+  int n_main = L.grid;
+  if (L.bounded) n_main = std::min(n_main, std::min(resident_ctas(kernel), RED_GRID));
+  return L.fh.n_pack + std::max(n_main, 1) + L.fh.n_bnd;
+}
+
+// MODE x DOT dispatch; F(mode_tag, dot_tag) launches one instantiation
+template <class F>
+void dispatch_mode(int mode, bool dot, F&& f) {
+#define PAMG_M(MD, DT) \
+  case MD:             \
+    f(std::integral_constant<int, MD>{}, std::integral_constant<bool, DT>{}); \
     break;
-  if (DOT) {
+  if (dot) {
     switch (mode) {
-      PAMG_M(M_MUL)
-      PAMG_M(M_JACOBI)
+      PAMG_M(M_MUL, true)
+      PAMG_M(M_JACOBI, true)
       default:
         throw std::runtime_error("fused dot only on MUL/JACOBI");
     }
   } else {
     switch (mode) {
-      PAMG_M(M_MUL)
-      PAMG_M(M_RESID)
-      PAMG_M(M_JACOBI)
-      PAMG_M(M_ADD)
-      PAMG_M(M_RESTRICT)
-      PAMG_M(M_CHEB)
+      PAMG_M(M_MUL, false)
+      PAMG_M(M_RESID, false)
+      PAMG_M(M_JACOBI, false)
+      PAMG_M(M_ADD, false)
+      PAMG_M(M_RESTRICT, false)
+      PAMG_M(M_CHEB, false)
       default:
         throw std::runtime_error("bad mode");
     }
@@ -456,60 +519,52 @@ void launch_spmv_mode(int mode, int lanes, int grid, cudaStream_t s, CsrView A, 
 #undef PAMG_M
 }
 
-void launch_stream(int mode, bool dot, int grid, cudaStream_t s, StreamView A, const double* x, const EpiArgs& a, DevState* st,
-                   double* partials, const RedCtx& rc, int publish, int slot) {
-#define PAMG_S(MD, DT)                                                                      \
-  k_spmv_stream<MD, DT><<<grid, BLOCK, 0, s>>>(A, x, a, st, partials, rc, publish, slot); \
-  break;
-  if (dot) {
-    switch (mode) {
-      case M_MUL: PAMG_S(M_MUL, true)
-      case M_JACOBI: PAMG_S(M_JACOBI, true)
-      default: throw std::runtime_error("fused dot only on MUL/JACOBI");
+void launch_csr(int mode, bool dot, int lanes, CsrView A, const LaunchArgs& L) {
+  dispatch_mode(mode, dot, [&](auto md, auto dt) {
+    constexpr int MD = decltype(md)::value;
+    constexpr bool DT = decltype(dt)::value;
+#define PAMG_L(LN)                                                                                                         \
+  case LN:                                                                                                                 \
+    k_spmv<LN, MD, DT><<<main_grid(L, (const void*)k_spmv<LN, MD, DT>), BLOCK, 0, L.s>>>(A, L.x, L.a, L.st, L.fh, L.partials, L.rc, \
+                                                                                        L.publish, L.slot);               \
+    break;
+    switch (lanes) {
+      PAMG_L(1)
+      PAMG_L(2)
+      PAMG_L(4)
+      PAMG_L(8)
+      PAMG_L(16)
+      PAMG_L(32)
+      default:
+        throw std::runtime_error("bad lanes_per_row");
     }
-  } else {
-    switch (mode) {
-      case M_MUL: PAMG_S(M_MUL, false)
-      case M_RESID: PAMG_S(M_RESID, false)
-      case M_JACOBI: PAMG_S(M_JACOBI, false)
-      case M_ADD: PAMG_S(M_ADD, false)
-      case M_RESTRICT: PAMG_S(M_RESTRICT, false)
-      case M_CHEB: PAMG_S(M_CHEB, false)
-      default: throw std::runtime_error("bad mode");
-    }
-  }
-#undef PAMG_S
+#undef PAMG_L
+  });
 }
 
-template <int RPT>
-void launch_sell_rpt(int mode, bool dot, int grid, cudaStream_t s, SellView A, const double* x, const EpiArgs& a, DevState* st,
-                     double* partials, const RedCtx& rc, int publish, int slot) {
-#define PAMG_E(MD, DT)                                                                         \
-  k_spmv_sell<RPT, MD, DT><<<grid, BLOCK, 0, s>>>(A, x, a, st, partials, rc, publish, slot); \
-  break;
-  if (dot) {
-    switch (mode) {
-      case M_MUL: PAMG_E(M_MUL, true)
-      case M_JACOBI: PAMG_E(M_JACOBI, true)
-      default: throw std::runtime_error("fused dot only on MUL/JACOBI");
-    }
-  } else {
-    switch (mode) {
-      case M_MUL: PAMG_E(M_MUL, false)
-      case M_RESID: PAMG_E(M_RESID, false)
-      case M_JACOBI: PAMG_E(M_JACOBI, false)
-      case M_ADD: PAMG_E(M_ADD, false)
-      case M_RESTRICT: PAMG_E(M_RESTRICT, false)
-      case M_CHEB: PAMG_E(M_CHEB, false)
-      default: throw std::runtime_error("bad mode");
-    }
-  }
-#undef PAMG_E
+void launch_stream(int mode, bool dot, StreamView A, const LaunchArgs& L) {
+  dispatch_mode(mode, dot, [&](auto md, auto dt) {
+    auto k = k_spmv_stream<decltype(md)::value, decltype(dt)::value>;
+    k<<<main_grid(L, (const void*)k), BLOCK, 0, L.s>>>(A, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
+  });
+}
+
+void launch_sell(int mode, bool dot, int rpt, SellView A, const LaunchArgs& L) {
+  dispatch_mode(mode, dot, [&](auto md, auto dt) {
+    auto k = rpt == 2 ? k_spmv_sell<2, decltype(md)::value, decltype(dt)::value> : k_spmv_sell<1, decltype(md)::value, decltype(dt)::value>;
+    k<<<main_grid(L, (const void*)k), BLOCK, 0, L.s>>>(A, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
+  });
+}
+
+void launch_boundary(int mode, bool dot, const LaunchArgs& L) {
+  dispatch_mode(mode, dot, [&](auto md, auto dt) {
+    k_boundary<decltype(md)::value, decltype(dt)::value><<<L.grid, BLOCK, 0, L.s>>>(L.x, L.a, L.st, L.fh, L.partials, L.rc, L.slot);
+  });
 }
 
 }  // namespace
 
-// One SpMV-family operation over all local parts:  [pack halo of xin] ; main (own-own) ; [own-ghost correction].
+// One SpMV-family operation over all local parts: consistent!(xin) + own rows of the operator.
 // which: PAMG_A_OO / PAMG_P_OO / PAMG_R_OO (the matching *_OG is implied).
 // row_level: level whose LevelDev holds the blocks; halo_level: level of the column partition.
 struct OpSpec {
@@ -530,6 +585,70 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   else
     need = I.need_halo_P[l];
   const bool exchange = need && !op.coarse_ghosts_local;
+  const bool fused = I.fused_halo;
+  const int wsel = op.which / 2;  // 0 A, 1 P, 2 R
+
+  auto halo_args = [&](PartDev& pd, bool with_pack, bool with_bnd) {
+    LevelDev& ld = *pd.lev[l];
+    LevelDev& hl = *pd.lev[op.halo_level];
+    FusedHalo fh{};
+    fh.level = op.halo_level;
+    fh.fixed_parity = op.coarse_ghosts_local ? 0 : -1;
+    fh.fused = fused ? 1 : 0;
+    fh.skip = need ? ld.bnd[wsel].skip.p : nullptr;
+    if (ld.bnd[wsel].n == 0) fh.skip = nullptr;
+    if (with_pack) {
+      fh.n_pack = std::max(1, std::min(32, (hl.n_send + BLOCK * 4 - 1) / (BLOCK * 4)));
+      fh.n_send = hl.n_send;
+      fh.n_nbrs = hl.n_send_nbrs;
+      fh.send_idx = hl.send_idx.p;
+      fh.nbrs = hl.send_nbrs.p;
+    }
+    if (with_bnd) {
+      const DevBnd& b = ld.bnd[wsel];
+      const int rpb = BLOCK / b.lanes;
+      fh.n_bnd = std::max(1, std::min(148, (b.n + rpb - 1) / rpb));
+      fh.B = b.view();
+      fh.hr = hl.hr;
+    }
+    return fh;
+  };
+  auto launch_main = [&](PartDev& pd, size_t i, const FusedHalo& fh, int publish) {
+    LevelDev& ld = *pd.lev[l];
+    const DevCsr& m = ld.blk[op.which];
+    LaunchArgs L{0, op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
+    L.fh.v = xin[i];
+    int n_main;
+    if (m.sell_rpt) {
+      n_main = (m.nslices + BLOCK / 32 - 1) / (BLOCK / 32);
+    } else if (m.stream) {
+      n_main = m.nblocks;
+    } else {
+      n_main = I.grid_for(m.nrows, (BLOCK / m.lanes) * 4);
+    }
+    L.grid = std::max(n_main, 1);
+    if (m.sell_rpt)
+      launch_sell(op.mode, op.dot, m.sell_rpt, m.slview(), L);
+    else if (m.stream)
+      launch_stream(op.mode, op.dot, m.sview(), L);
+    else
+      launch_csr(op.mode, op.dot, m.lanes, m.view(), L);
+    I.note_launch();
+  };
+
+  if (fused) {  // one launch per part: pack + main + boundary roles
+    for (size_t i = 0; i < I.parts.size(); ++i) {
+      PartDev& pd = I.P(i);
+      LevelDev& hl = *pd.lev[op.halo_level];
+      const bool nbrs = hl.n_recv_nbrs > 0 || hl.n_send_nbrs > 0;
+      I.set_dev(pd);
+      const FusedHalo fh = halo_args(pd, exchange && nbrs, need && nbrs);
+      launch_main(pd, i, fh, 1);
+    }
+    CK(cudaGetLastError());
+    return;
+  }
+  // split: three phases over all parts so that no kernel waits for a later kernel of its own stream
   // phase 1: producers (never wait)
   if (exchange)
     for (size_t i = 0; i < I.parts.size(); ++i) {
@@ -541,62 +660,25 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
                                                                              hl.n_send_nbrs, pd.st.p, op.halo_level);
       I.note_launch();
     }
-  // phase 2: own-own
+  // phase 2: all rows of the own-own block (boundary rows are computed but not stored)
   for (size_t i = 0; i < I.parts.size(); ++i) {
     PartDev& pd = I.P(i);
-    LevelDev& ld = *pd.lev[l];
     LevelDev& hl = *pd.lev[op.halo_level];
-    const DevCsr& m = ld.blk[op.which];
-    const bool og_follows = need && hl.n_recv_nbrs > 0;
+    const bool bnd_follows = need && hl.n_recv_nbrs > 0;
     I.set_dev(pd);
-    if (m.sell_rpt) {
-      const int wpb = BLOCK / 32;
-      int grid = (m.nslices + wpb - 1) / wpb;
-      if (op.dot) grid = std::min(grid, RED_GRID);
-      grid = std::max(grid, 1);
-      if (m.sell_rpt == 2)
-        launch_sell_rpt<2>(op.mode, op.dot, grid, pd.stream, m.slview(), xin[i], epi[i], pd.st.p, pd.partials.p, pd.rc,
-                           og_follows ? 0 : 1, op.slot);
-      else
-        launch_sell_rpt<1>(op.mode, op.dot, grid, pd.stream, m.slview(), xin[i], epi[i], pd.st.p, pd.partials.p, pd.rc,
-                           og_follows ? 0 : 1, op.slot);
-      I.note_launch();
-      continue;
-    }
-    if (m.stream) {
-      launch_stream(op.mode, op.dot, op.dot ? std::min(m.nblocks, RED_GRID) : m.nblocks, pd.stream, m.sview(), xin[i], epi[i],
-                    pd.st.p, pd.partials.p, pd.rc, og_follows ? 0 : 1, op.slot);
-      I.note_launch();
-      continue;
-    }
-    const int rpb = BLOCK / m.lanes;
-    const int grid = I.grid_for(m.nrows, rpb * 4);
-    if (op.dot)
-      launch_spmv_mode<true, false>(op.mode, m.lanes, grid, pd.stream, m.view(), xin[i], epi[i], pd.st.p, hl.hr, op.halo_level,
-                                    -1, pd.partials.p, pd.rc, og_follows ? 0 : 1, op.slot);
-    else
-      launch_spmv_mode<false, false>(op.mode, m.lanes, grid, pd.stream, m.view(), xin[i], epi[i], pd.st.p, hl.hr,
-                                     op.halo_level, -1, pd.partials.p, pd.rc, 0, 0);
-    I.note_launch();
+    const FusedHalo fh = halo_args(pd, false, false);
+    launch_main(pd, i, fh, bnd_follows ? 0 : 1);
   }
-  // phase 3: own-ghost correction (consumers: wait for the neighbours' flags)
+  // phase 3: boundary rows (consumers: wait for the neighbours' flags)
   if (need)
     for (size_t i = 0; i < I.parts.size(); ++i) {
       PartDev& pd = I.P(i);
-      LevelDev& ld = *pd.lev[l];
       LevelDev& hl = *pd.lev[op.halo_level];
       if (hl.n_recv_nbrs == 0) continue;
-      const DevCsr& m = ld.blk[op.which + 1];
       I.set_dev(pd);
-      const int rpb = BLOCK / m.lanes;
-      const int grid = I.grid_for(std::max(m.nrows, 1), rpb);
-      const int fixed = op.coarse_ghosts_local ? 0 : -1;
-      if (op.dot)
-        launch_spmv_mode<true, true>(op.mode, m.lanes, grid, pd.stream, m.view(), nullptr, epi[i], pd.st.p, hl.hr,
-                                     op.halo_level, fixed, pd.partials.p, pd.rc, 1, op.slot);
-      else
-        launch_spmv_mode<false, true>(op.mode, m.lanes, grid, pd.stream, m.view(), nullptr, epi[i], pd.st.p, hl.hr,
-                                      op.halo_level, fixed, pd.partials.p, pd.rc, 0, 0);
+      const FusedHalo fh = halo_args(pd, false, true);
+      LaunchArgs L{fh.n_bnd, false, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, 1, op.slot};
+      launch_boundary(op.mode, op.dot, L);
       I.note_launch();
     }
   CK(cudaGetLastError());
@@ -665,11 +747,11 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       LevelDev& ld = *pd.lev.back();
       ld.n_own = pl.n_own;
       ld.n_ghost = pl.n_ghost;
-      for (int b = 0; b < 6; ++b) {
-        const bool og = (b & 1);
+      for (int b = 0; b < 6; b += 2) {
         int lanes = 0;
-        if (!og && b == PAMG_A_OO && o.lanes_per_row > 0) lanes = o.lanes_per_row;
-        build_csr(pl.blk[b], og, ld.blk[b], og ? 4 : lanes, og ? PAMG_FORMAT_CSR : o.spmv_format, o, b);
+        if (b == PAMG_A_OO && o.lanes_per_row > 0) lanes = o.lanes_per_row;
+        build_csr(pl.blk[b], false, ld.blk[b], lanes, o.spmv_format, o, b);
+        build_bnd(pl.blk[b], pl.blk[b + 1], ld.bnd[b / 2]);
         max_blocks = std::max(max_blocks, ld.blk[b].nblocks);
       }
       // smoother weights
@@ -724,7 +806,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         ld.asm_flags = (const uint32_t*)(pd.arena + pd.lay.asm_flags[l]);
       }
     }
-    pd.partials.alloc((size_t)max_blocks + 64);  // one partial per CTA of a fused-reduction kernel
+    pd.partials.alloc((size_t)max_blocks + 512);  // one partial per CTA of a fused-reduction kernel
     // coarsest solve data
     const PartLevel& pc = h->levels[I.L - 1].parts[part];
     pd.inv.upload(h->coarse_inv);
@@ -743,6 +825,21 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   CK(cudaMallocHost(&I.pinned, sizeof(DevState) * Impl::RING));
   for (int k = 0; k < Impl::RING; ++k) CK(cudaEventCreateWithFlags(&I.ring_ev[k], cudaEventDisableTiming));
   plan_buffers();
+  {  // fused halo roles need every local part alone on its device (a kernel may then wait for its peers)
+    std::map<int, int> per_dev;
+    for (auto& up : I.parts) per_dev[up->device]++;
+    bool alone = true;
+    for (auto& kv : per_dev) alone = alone && kv.second == 1;
+    bool symmetric = true;  // every part both sends to and receives from its neighbours on every level
+    for (int l = 0; l < I.L; ++l)
+      for (int p = 0; p < I.nparts; ++p) {
+        const PartLevel& pl = h->levels[l].parts[p];
+        if (pl.recv.empty() != pl.send.empty()) symmetric = false;
+      }
+    const char* env = getenv("PAMG_FUSE_HALO");
+    const bool want = env ? atoi(env) != 0 : o.fuse_halo != 0;
+    I.fused_halo = want && alone && symmetric;
+  }
   if (nlocal == I.nparts) connect();
 }
 
@@ -1678,6 +1775,7 @@ void Engine::get_stats(pamg_stats* s) {
   Impl& I = *impl;
   *s = I.stats;
   s->n_levels = I.L;
+  s->fused_halo = I.fused_halo ? 1 : 0;
   auto fmt_of = [](const DevCsr& m) { return m.sell_rpt ? PAMG_FORMAT_SELL : m.stream ? PAMG_FORMAT_STREAM : PAMG_FORMAT_CSR; };
   for (int l = 0; l < 16; ++l) {
     const bool have = l < I.L && !I.parts.empty();

@@ -5,17 +5,24 @@
 //   a2 smoothing       out = x + w (b - A x)           (+ fused dot(r, z) on level 0)
 //   a3 residual        out = b - A x ;  restrict  b_c = R r  (+ fused coarse pre-smooth x_c = w_c b_c)
 //   a4 prolong+correct out = x + P e_c
-// so one templated kernel family covers them; the own-ghost block of the PSparseMatrix split
-// format (mul!: c_own = A_oo b_own; wait(consistent!); c_own += A_og b_ghost)
-// is a second, short "correction" launch over boundary rows only that first waits for the
-// halo flags written by the neighbouring GPUs.
+// so one templated kernel family (three storage formats) covers them.
 //
-// Cross-GPU data movement is done by these kernels themselves over NVLink peer mappings:
-// halo_pack stores boundary values straight into the neighbours' ghost staging buffers and
-// then publishes an epoch flag (release, system scope); consumers spin on their local flag
-// (acquire).  Staging buffers are double-buffered by epoch parity; see DESIGN.md "Halo
-// protocol" for why that is race-free.  Producers never wait, only consumers do, so several
-// parts may share one GPU and one stream (the "debug backend" layout) without deadlock.
+// Halo exchange (PartitionedArrays mul!: start consistent!(b); c_own = A_oo b_own; wait;
+// c_own += A_og b_ghost) is FUSED INTO THE SAME KERNEL as three CTA roles:
+//   pack CTAs     (lowest block ids)  store this part's boundary values straight into the neighbour
+//                                     GPUs' ghost staging over NVLink peer mappings, then publish an
+//                                     epoch flag (release, system scope);
+//   main CTAs                         all rows of the own-own block; rows that also have ghost columns
+//                                     ("boundary rows", marked in `skip`) are computed but not stored;
+//   boundary CTAs (highest block ids) spin on the local flags (acquire) -- by the time they are
+//                                     dispatched the interior work has hidden the NVLink latency --
+//                                     and compute the boundary rows completely: own columns then
+//                                     ghost columns, then the epilogue.
+// Staging buffers are double-buffered by epoch parity; see DESIGN.md "Halo protocol" for why that
+// is race-free.  When several parts share one GPU (the PartitionedArrays "debug backend" layout
+// used by the single-GPU tests) a kernel must never wait for a later kernel of the same stream, so
+// the same three roles run as three launches (k_halo_pack, main, k_boundary): identical row
+// arithmetic, identical results.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -57,6 +64,7 @@ struct DevState {
   uint32_t red_epoch;
   uint32_t coarse_epoch;
   uint32_t halo_epoch[MAX_LEVELS];
+  uint32_t pack_done[MAX_LEVELS];  // fused launches: epoch whose pack role has finished
   uint32_t asm_epoch[MAX_LEVELS];
   uint32_t ticket[8];
   int32_t done;
@@ -89,6 +97,32 @@ struct HaloRecv {
   int32_t n_nbrs;
 };
 
+// boundary rows of one operator: the rows of the own-own block that also have own-ghost entries,
+// stored whole: entries [ptr[k], mid[k]) index the own vector, [mid[k], ptr[k+1]) the ghost staging
+struct BndView {
+  const int32_t* rows;  // [n] own-local row ids
+  const int32_t* ptr;   // [n + 1]
+  const int32_t* mid;   // [n]
+  const int32_t* col;
+  const double* val;
+  int32_t n, lanes;     // lanes: threads per row (power of two <= 32)
+};
+
+// what the pack / boundary roles of a fused launch need (n_pack == n_bnd == 0: plain kernel)
+struct FusedHalo {
+  int32_t n_pack, n_bnd;    // CTAs per role; the main role gets gridDim.x - n_pack - n_bnd
+  int32_t level;            // halo level (epoch / flag index)
+  int32_t fixed_parity;     // >= 0: ghost values are already in staging[parity], no wait (coarsest level)
+  int32_t fused;            // 1: roles inside one launch (boundary role advances the epoch)
+  int32_t n_send, n_nbrs;   // pack role
+  const double* v;
+  const int32_t* send_idx;
+  const SendNbr* nbrs;
+  BndView B;                // boundary role
+  HaloRecv hr;
+  const uint8_t* skip;      // [nrows] 1 => boundary row: the main role must not store it (nullptr: none)
+};
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
@@ -109,14 +143,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ldg_stream(const int32_t* p) { return __ldcs(p); }
 
-// Load that the compiler may not sink to its use: the epilogue operands of a row are requested BEFORE
-// the row's entries are streamed, so their latency overlaps the main loop (without this nvcc moves the
-// loads below the loop and the SELL Jacobi sweep runs 2x slower than the plain SpMV; gpurun sweep r01).
-__device__ __forceinline__ double ld_early(const double* p) {
-  double v;
-  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
+// Request a line without tying up a register: the epilogue operands of a row (b, w, ...) are prefetched
+// into L1 BEFORE the row's entries are streamed and loaded after the loop, when they hit.  (Holding them
+// in registers across the loop costs the SELL kernels their load-level parallelism: 0.49 vs 0.40 ms for
+// the 256^3 Jacobi sweep; letting nvcc sink the loads below the loop exposes a full DRAM latency.)
+__device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t e, DevState* st) {
   if ((int32_t)(ld_acquire_sys(flag) - e) >= 0) return;
@@ -163,19 +194,20 @@ __device__ __forceinline__ double block_sum(double v) {
 
 // last-block detection: returns true (in every thread of exactly one block) once all blocks of
 // the grid have passed; the ticket is reset for the next launch.
-__device__ __forceinline__ bool last_block(uint32_t* ticket) {
+__device__ __forceinline__ bool last_block_n(uint32_t* ticket, uint32_t n) {
   __shared__ bool is_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const uint32_t t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    is_last = (t == n - 1);
     if (is_last) *ticket = 0;
   }
   __syncthreads();
   if (is_last) __threadfence();
   return is_last;
 }
+__device__ __forceinline__ bool last_block(uint32_t* ticket) { return last_block_n(ticket, gridDim.x); }
 
 // publish v[0..RED_W) to every part (one thread)
 __device__ __forceinline__ void red_publish(DevState* st, const RedCtx& rc, const double* v) {
@@ -227,131 +259,8 @@ __device__ __forceinline__ void dot_finish(double acc, double* partials, DevStat
 }
 
 // ---------------------------------------------------------------------------------------------
-// SpMV family.  LANES threads per row; OG = own-ghost correction pass (x = ghost staging).
+// row epilogue shared by every SpMV family and by the boundary role
 // ---------------------------------------------------------------------------------------------
-template <int MODE, bool OG>
-__device__ __forceinline__ double apply_epilogue(const EpiArgs& a, int row, double s) {
-  double res;
-  if (!OG) {
-    if (MODE == M_MUL) {
-      res = s;
-      a.out[row] = res;
-    } else if (MODE == M_RESID) {
-      res = a.in0[row] - s;
-      a.out[row] = res;
-    } else if (MODE == M_JACOBI) {
-      res = a.in1[row] + a.w[row] * (a.in0[row] - s);
-      a.out[row] = res;
-    } else if (MODE == M_ADD) {
-      res = a.in0[row] + s;
-      a.out[row] = res;
-    } else if (MODE == M_RESTRICT) {
-      res = s;
-      a.out[row] = res;
-      if (a.out2) a.out2[row] = a.w[row] * s;
-    } else {  // M_CHEB
-      const double d = a.c1 * (a.aux ? a.aux[row] : 0.0) + a.c2 * (a.w[row] * (a.in0[row] - s));
-      a.out2[row] = d;
-      res = a.in1[row] + d;
-      a.out[row] = res;
-    }
-    return res;
-  } else {  // correction: the main pass already stored its result; returns the CHANGE of out[row]
-    double delta;
-    if (MODE == M_MUL || MODE == M_ADD) {
-      delta = s;
-    } else if (MODE == M_RESID) {
-      delta = -s;
-    } else if (MODE == M_JACOBI) {
-      delta = -(a.w[row] * s);
-    } else if (MODE == M_RESTRICT) {
-      delta = s;
-      if (a.out2) a.out2[row] += a.w[row] * s;
-    } else {  // M_CHEB
-      delta = -(a.c2 * (a.w[row] * s));
-      a.out2[row] += delta;
-    }
-    a.out[row] += delta;
-    return delta;
-  }
-}
-
-template <int LANES, int MODE, bool DOT, bool OG>
-__global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restrict__ x, EpiArgs a, DevState* st,
-                                                 HaloRecv hr, int level, int fixed_parity, double* partials, RedCtx rc,
-                                                 int publish, int red_slot) {
-  if (st->done) return;
-  if (OG) {  // wait for the neighbours' halo of this level, then read the staging of that parity
-    __shared__ int s_par;
-    if (threadIdx.x == 0) {
-      if (fixed_parity >= 0) {
-        s_par = fixed_parity;
-      } else {
-        const uint32_t e = *(volatile uint32_t*)&st->halo_epoch[level];
-        s_par = halo_wait(hr, e, st);
-      }
-    }
-    __syncthreads();
-    x = hr.ghost[s_par];
-  }
-  constexpr int RPB = BLOCK / LANES;
-  const int lane = threadIdx.x % LANES;
-  const int grp = threadIdx.x / LANES;
-  double acc = 0.0;
-  // block-uniform trip count: every lane of a warp reaches the full-mask shuffles below, rows past
-  // the end are just predicated off (a lane that skipped the loop would deadlock the shuffle)
-  for (int r0 = blockIdx.x * RPB; r0 < A.nrows; r0 += gridDim.x * RPB) {
-    const int r = r0 + grp;
-    const bool valid = r < A.nrows;
-    int beg = 0, end = 0;
-    if (valid) {
-      beg = A.ptr[r];
-      end = A.ptr[r + 1];
-    }
-    double s = 0.0;
-    for (int k = beg + lane; k < end; k += LANES) {
-      const int c = ldg_stream(A.col + k);
-      const double v = ldg_stream(A.val + k);
-      s += v * (OG ? __ldcv(x + c) : x[c]);
-    }
-    s = group_sum<LANES>(s);
-    if (valid && lane == 0) {
-      const int row = A.rows ? A.rows[r] : r;
-      const double res = apply_epilogue<MODE, OG>(a, row, s);
-      if (DOT) acc += a.dotv[row] * res;
-    }
-  }
-  if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, OG ? 1 : 0, red_slot);
-}
-
-// ---------------------------------------------------------------------------------------------
-// CSR-stream SpMV family (the fast path for the own-own blocks).
-//
-// The vector kernel above is latency-bound on short rows (ncu, profiles/r01: ~18 % DRAM
-// throughput at full occupancy, long-scoreboard stalls: a serial ptr -> col/val -> x chain with
-// ~12 B in flight per thread).  Here a CTA owns a run of consecutive rows whose entries fit the
-// shared-memory product buffer; the run's val/col ranges are CONTIGUOUS in CSR, so phase A streams
-// them with fully coalesced 128-bit loads (int4 of 4 column ids + 2 x double2 of values per thread
-// and step, all steps issued back to back: up to 144 B in flight per thread), gathers x through
-// L1/L2 and parks the products in shared memory; phase B sums each row's products in column order
-// (one thread per row) and applies the fused epilogue, whose operands were prefetched before
-// phase A.  Products are rounded before they are added (no FMA across the smem round trip), so a
-// row sum is bit-identical to the oracle's sequential `s += a_ij * x_j`.
-// ---------------------------------------------------------------------------------------------
-constexpr int S_CAP = 3072;        // entries per row block (24 KB of fp64 products)
-constexpr int S_CHUNKS = 4;        // phase B handles up to S_CHUNKS rows per thread
-constexpr int S_ROWS = S_CHUNKS * BLOCK;  // rows per row block
-constexpr int S_STEPS = (S_CAP + 4 * BLOCK - 1) / (4 * BLOCK);
-constexpr int RED_GRID = 148 * 8;  // CTAs of a kernel with a fused reduction (one fence + ticket per CTA)
-
-struct StreamView {
-  const int2* blk;     // [nblocks + 1] {first row, first entry} of each row block
-  const int32_t* ptr;
-  const int32_t* col;  // padded with zeros to a multiple of 4 entries (+ 8)
-  const double* val;
-  int32_t nrows, nblocks;
-};
-
 template <int MODE>
 __device__ __forceinline__ double stream_epilogue(const EpiArgs& a, int row, double s, double e_in0, double e_in1, double e_w,
                                                   double e_aux) {
@@ -381,18 +290,203 @@ __device__ __forceinline__ double stream_epilogue(const EpiArgs& a, int row, dou
   return res;
 }
 
+template <int MODE>
+__device__ __forceinline__ double apply_epilogue(const EpiArgs& a, int row, double s) {
+  double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0;
+  if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
+  if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
+  if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
+  if (MODE == M_CHEB && a.aux) e_aux = a.aux[row];
+  return stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo roles (consistent! fused into the consuming kernel)
+// ---------------------------------------------------------------------------------------------
+// pack role, CTA `bid` of fh.n_pack: owner -> ghost stores into the neighbours' staging, then flags
+__device__ __forceinline__ void pack_role(const FusedHalo& fh, DevState* st, int bid) {
+  const uint32_t e = *(volatile uint32_t*)&st->halo_epoch[fh.level] + 1u;
+  const int par = (int)(e & 1u);
+  for (int k = bid * BLOCK + threadIdx.x; k < fh.n_send; k += fh.n_pack * BLOCK) {
+    int nb = 0;
+    while (nb + 1 < fh.n_nbrs && k >= fh.nbrs[nb + 1].offset) ++nb;
+    fh.nbrs[nb].ghost[par][k - fh.nbrs[nb].offset] = fh.v[fh.send_idx[k]];
+  }
+  __threadfence_system();
+  if (last_block_n(&st->ticket[1], (uint32_t)fh.n_pack)) {
+    __threadfence_system();
+    if (threadIdx.x < fh.n_nbrs) st_release_sys(fh.nbrs[threadIdx.x].flag, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (fh.fused)
+        *(volatile uint32_t*)&st->pack_done[fh.level] = e;  // the boundary role advances the epoch
+      else
+        st->halo_epoch[fh.level] = e;
+    }
+  }
+}
+
+// boundary role, CTA `bid` of fh.n_bnd: wait for the neighbours' halo, then the boundary rows whole
+// (own columns, then ghost columns, then the epilogue).  Returns this thread's dot contribution.
+template <int MODE, bool DOT>
+__device__ __forceinline__ double boundary_role(const FusedHalo& fh, const double* __restrict__ x, const EpiArgs& a, DevState* st,
+                                                int bid) {
+  __shared__ int s_par;
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    if (fh.fixed_parity >= 0) {
+      s_par = fh.fixed_parity;
+      s_epoch = 0;
+    } else {
+      const uint32_t e = *(volatile uint32_t*)&st->halo_epoch[fh.level] + (fh.fused ? 1u : 0u);
+      s_par = halo_wait(fh.hr, e, st);
+      s_epoch = e;
+    }
+  }
+  __syncthreads();
+  const double* g = fh.hr.ghost[s_par];
+  const BndView& B = fh.B;
+  const int lanes = B.lanes;
+  const int lane = threadIdx.x & (lanes - 1);
+  const int grp = threadIdx.x / lanes;
+  const int rpb = BLOCK / lanes;
+  double acc = 0.0;
+  // block-uniform trip count: every lane reaches the full-mask shuffles
+  for (int k0 = bid * rpb; k0 < B.n; k0 += fh.n_bnd * rpb) {
+    const int k = k0 + grp;
+    const bool valid = k < B.n;
+    int beg = 0, mid = 0, end = 0;
+    if (valid) {
+      beg = B.ptr[k];
+      mid = B.mid[k];
+      end = B.ptr[k + 1];
+    }
+    double s = 0.0, sg = 0.0;
+    for (int q = beg + lane; q < mid; q += lanes) s += ldg_stream(B.val + q) * x[ldg_stream(B.col + q)];
+    for (int q = mid + lane; q < end; q += lanes) sg += ldg_stream(B.val + q) * __ldcv(g + ldg_stream(B.col + q));
+    for (int o = lanes >> 1; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    }
+    if (valid && lane == 0) {
+      const int row = B.rows[k];
+      const double res = apply_epilogue<MODE>(a, row, s + sg);  // mul!: own-own sum, then += own-ghost sum
+      if (DOT) acc += a.dotv[row] * res;
+    }
+  }
+  if (fh.fused && fh.fixed_parity < 0 && last_block_n(&st->ticket[4], (uint32_t)fh.n_bnd)) {
+    if (threadIdx.x == 0) {  // every boundary CTA has consumed epoch e: advance once the local pack is out
+      const uint32_t e = s_epoch;
+      if (fh.n_pack > 0) spin_until(&st->pack_done[fh.level], e, st);
+      *(volatile uint32_t*)&st->halo_epoch[fh.level] = e;
+    }
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sub-warp CSR ("vector per row") SpMV family: LANES threads per row (32 = warp per row)
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
+                                                 double* partials, RedCtx rc, int publish, int red_slot) {
+  if (st->done) return;
+  double acc = 0.0;
+  int bid = blockIdx.x;
+  const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
+  if (bid < fh.n_pack) {
+    pack_role(fh, st, bid);
+  } else if (bid >= fh.n_pack + n_main) {
+    acc = boundary_role<MODE, DOT>(fh, x, a, st, bid - fh.n_pack - n_main);
+  } else {
+    bid -= fh.n_pack;
+    constexpr int RPB = BLOCK / LANES;
+    const int lane = threadIdx.x % LANES;
+    const int grp = threadIdx.x / LANES;
+    // block-uniform trip count: every lane of a warp reaches the full-mask shuffles below, rows past
+    // the end are just predicated off (a lane that skipped the loop would deadlock the shuffle)
+    for (int r0 = bid * RPB; r0 < A.nrows; r0 += n_main * RPB) {
+      const int r = r0 + grp;
+      const bool valid = r < A.nrows;
+      int beg = 0, end = 0;
+      if (valid) {
+        beg = A.ptr[r];
+        end = A.ptr[r + 1];
+      }
+      double s = 0.0;
+      for (int k = beg + lane; k < end; k += LANES) {
+        const int c = ldg_stream(A.col + k);
+        const double v = ldg_stream(A.val + k);
+        s += v * x[c];
+      }
+      s = group_sum<LANES>(s);
+      if (valid && lane == 0 && !(fh.skip && fh.skip[r])) {
+        const double res = apply_epilogue<MODE>(a, r, s);
+        if (DOT) acc += a.dotv[r] * res;
+      }
+    }
+  }
+  if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+}
+
+// boundary role as its own launch (several parts on one GPU); completes a dot started by the main launch
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK) k_boundary(const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
+                                                     double* partials, RedCtx rc, int red_slot) {
+  if (st->done) return;
+  const double acc = boundary_role<MODE, DOT>(fh, x, a, st, blockIdx.x);
+  if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, 1, 1, red_slot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR-stream SpMV family (the fast path for the own-own blocks).
+//
+// The vector kernel above is latency-bound on short rows (ncu, profiles/r01: ~18 % DRAM
+// throughput at full occupancy, long-scoreboard stalls: a serial ptr -> col/val -> x chain with
+// ~12 B in flight per thread).  Here a CTA owns a run of consecutive rows whose entries fit the
+// shared-memory product buffer; the run's val/col ranges are CONTIGUOUS in CSR, so phase A streams
+// them with fully coalesced 128-bit loads (int4 of 4 column ids + 2 x double2 of values per thread
+// and step, all steps issued back to back: up to 144 B in flight per thread), gathers x through
+// L1/L2 and parks the products in shared memory; phase B sums each row's products in column order
+// (one thread per row) and applies the fused epilogue, whose operands were prefetched before
+// phase A.  Products are rounded before they are added (no FMA across the smem round trip), so a
+// row sum is bit-identical to the oracle's sequential `s += a_ij * x_j`.
+// ---------------------------------------------------------------------------------------------
+constexpr int S_CAP = 3072;        // entries per row block (24 KB of fp64 products)
+constexpr int S_CHUNKS = 4;        // phase B handles up to S_CHUNKS rows per thread
+constexpr int S_ROWS = S_CHUNKS * BLOCK;  // rows per row block
+constexpr int S_STEPS = (S_CAP + 4 * BLOCK - 1) / (4 * BLOCK);
+constexpr int RED_GRID = 148 * 8;  // upper bound of the CTAs of a kernel with a fused reduction (one fence + ticket per CTA)
+
+struct StreamView {
+  const int2* blk;     // [nblocks + 1] {first row, first entry} of each row block
+  const int32_t* ptr;
+  const int32_t* col;  // padded with zeros to a multiple of 4 entries (+ 8)
+  const double* val;
+  int32_t nrows, nblocks;
+};
+
 // The grid is the number of row blocks (one block per CTA, hardware-scheduled) except for the
 // variants with a fused dot product, which run RED_GRID CTAs that stride over the row blocks: a
 // gpu-scope fence per CTA (needed by the last-block reduction) invalidates the SM's L1, so it must
 // not happen once per row block (ncu r01: +45 % time with 65536 fencing CTAs).
 template <int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const double* __restrict__ x, EpiArgs a, DevState* st,
-                                                        double* partials, RedCtx rc, int publish, int red_slot) {
+                                                        FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
   __shared__ double prod[S_STEPS * 4 * BLOCK];
   const int t = threadIdx.x;
   double acc = 0.0;
-  for (int bk = blockIdx.x; bk < A.nblocks; bk += gridDim.x) {
+  const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
+  int bk0 = (int)blockIdx.x - fh.n_pack;
+  if ((int)blockIdx.x < fh.n_pack) {
+    pack_role(fh, st, blockIdx.x);
+    bk0 = A.nblocks;  // no main work
+  } else if (bk0 >= n_main) {
+    acc = boundary_role<MODE, DOT>(fh, x, a, st, bk0 - n_main);
+    bk0 = A.nblocks;
+  }
+  for (int bk = bk0; bk < A.nblocks; bk += n_main) {
     const int2 b0 = A.blk[bk], b1 = A.blk[bk + 1];
     const int r0 = b0.x, nr = b1.x - b0.x;
     const int ea = b0.y & ~3;              // 4-entry aligned start: 16 B (col) / 32 B (val) aligned
@@ -457,11 +551,13 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
         }
         double s = 0.0;
         for (int k = pb; k < pe; ++k) s += prod[k];
-        const double res = stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
-        if (DOT) acc += e_dot * res;
+        if (!(fh.skip && fh.skip[row])) {
+          const double res = stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
+          if (DOT) acc += e_dot * res;
+        }
       }
     }
-    if (bk + (int)gridDim.x < A.nblocks) __syncthreads();  // prod is reused by the next row block
+    if (bk + n_main < A.nblocks) __syncthreads();  // prod is reused by the next row block
   }
   if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }
@@ -505,33 +601,43 @@ __device__ __forceinline__ int sv_get(const int2& v, int k) { return k ? v.y : v
 
 template <int RPT, int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView A, const double* __restrict__ x, EpiArgs a, DevState* st,
-                                                      double* partials, RedCtx rc, int publish, int red_slot) {
+                                                      FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
+  const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
+  const int bid = (int)blockIdx.x - fh.n_pack;
+  if (bid < 0 || bid >= n_main) {  // halo roles
+    double racc = 0.0;
+    if (bid < 0)
+      pack_role(fh, st, blockIdx.x);
+    else
+      racc = boundary_role<MODE, DOT>(fh, x, a, st, bid - n_main);
+    if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+    return;
+  }
   using V = typename SellVec<RPT>::V;
   using I = typename SellVec<RPT>::I;
   constexpr int U = RPT == 1 ? 8 : 4;  // entries of a row in flight per step
   const int lane = threadIdx.x & 31;
   const int wpb = BLOCK / 32;
   double acc = 0.0;
-  for (int sl = blockIdx.x * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += gridDim.x * wpb) {
+  for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
     const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
     const int slot0 = sl * (32 * RPT) + lane * RPT;
     int row[RPT];
-    double e_in0[RPT], e_in1[RPT], e_w[RPT], e_aux[RPT], e_dot[RPT], s[RPT];
+    double s[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       const int slot = slot0 + k;
       row[k] = -1;
-      e_in0[k] = e_in1[k] = e_w[k] = e_aux[k] = e_dot[k] = 0.0;
       s[k] = 0.0;
       if (slot < A.nrows) {
         const int r = A.perm ? A.perm[slot] : slot;
+        if (fh.skip && fh.skip[r]) continue;
         row[k] = r;
-        if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0[k] = ld_early(a.in0 + r);
-        if (MODE == M_JACOBI || MODE == M_CHEB) e_in1[k] = ld_early(a.in1 + r);
-        if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w[k] = ld_early(a.w + r);
-        if (MODE == M_CHEB && a.aux) e_aux[k] = ld_early(a.aux + r);
-        if (DOT) e_dot[k] = ld_early(a.dotv + r);
+        if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) prefetch_l1(a.in0 + r);
+        if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) prefetch_l1(a.w + r);
+        if (MODE == M_CHEB && a.aux) prefetch_l1(a.aux + r);
+        if (DOT && a.dotv != a.in0) prefetch_l1(a.dotv + r);
       }
     }
     const V* __restrict__ vp = reinterpret_cast<const V*>(A.val) + (size_t)o0 * 32 + lane;
@@ -562,8 +668,8 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
 #pragma unroll
     for (int k = 0; k < RPT; ++k)
       if (row[k] >= 0) {
-        const double res = stream_epilogue<MODE>(a, row[k], s[k], e_in0[k], e_in1[k], e_w[k], e_aux[k]);
-        if (DOT) acc += e_dot[k] * res;
+        const double res = apply_epilogue<MODE>(a, row[k], s[k]);
+        if (DOT) acc += a.dotv[row[k]] * res;
       }
   }
   if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);

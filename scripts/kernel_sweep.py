@@ -31,6 +31,7 @@ rng = np.random.default_rng(1)
 b = c.host_matvec_global(rng.uniform(-1, 1, n))
 
 CONFIGS = {
+    "auto": dict(spmv_format=L.FORMAT_AUTO),
     "csr": dict(spmv_format=L.FORMAT_CSR),
     "stream": dict(spmv_format=L.FORMAT_STREAM),
     "sell1": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=1, sell_sigma=1),

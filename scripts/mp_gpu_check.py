@@ -20,14 +20,19 @@ def main():
     from parallel_amg_b200.distributed import connect_parts
     from util import det_vector, product_options
     pp = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
-    for dims, oopts in (((24, 20, 16), {}), ((40, 40, 40), {}), ((24, 20, 16), {"smoother": "chebyshev", "cheb_degree": 2})):
+    cases = (((24, 20, 16), {}, {}), ((40, 40, 40), {}, {}), ((24, 20, 16), {"smoother": "chebyshev", "cheb_degree": 2}, {}),
+             ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL)), ((24, 20, 16), {}, dict(spmv_format=L.FORMAT_CSR)),
+             ((40, 40, 40), {"smoother": "l1jacobi"}, dict(spmv_format=L.FORMAT_SELL, sell_sigma=128, sell_rows_per_thread=1)),
+             ((24, 20, 16), {}, dict(fuse_halo=0)))
+    for dims, oopts, kopts in cases:
         A = O.poisson_fd(dims)
         owner = O.uniform_partition(pp, dims)
         h = O.build(A, owner, world, oopts)
         c = L.Context(world)
         c.gallery_poisson(dims, pp)
-        c.setup(product_options(c, oopts))
+        c.setup(product_options(c, oopts, **kopts))
         connect_parts(c, rank, world, local)
+        assert c.stats().fused_halo == kopts.get("fuse_halo", 1)
         n = A.shape[0]
         lev = h["levels"][0]
         mine = lev["parts"][rank]["own_to_global"]
