@@ -66,7 +66,8 @@ typedef struct {
   int32_t spmv_format;    /* PAMG_FORMAT_* ; AUTO decides per level and per operator (A, P, R) */
   int32_t use_graph;      /* 1: replay the V-cycle / PCG iteration as CUDA graphs */
   int32_t lanes_per_row;  /* 0: auto (from mean nnz/row); else 1,2,4,8,16,32 for CSR */
-  int32_t tail_rows;      /* levels whose global rows <= this run inside one fused tail kernel (0: off) */
+  int32_t tail_rows;      /* coarse-level agglomeration: levels (>= 1) whose global rows <= this are merged over all
+                             parts and run replicated on every GPU without halos (0: only the coarsest level) */
   int32_t sell_sigma;     /* SELL sorting window in rows; 0: auto (1 = no sorting when the padding is small) */
   int32_t sell_rows_per_thread; /* 1 or 2 (C = 32 or 64; 2 => 128-bit value loads); 0: auto */
   int32_t fuse_halo;      /* 1: halo pack / wait / boundary rows run inside the consuming kernel whenever every local
@@ -98,6 +99,7 @@ typedef struct {
   int32_t format_r[16];
   double sell_fill[16];   /* stored entries / nnz of A's SELL layout (1.0 when A is not SELL) */
   int32_t fused_halo;     /* 1 when the halo roles run inside the consuming kernels */
+  int32_t tail_level;     /* first level of the replicated coarse tail (n_levels - 1: coarsest only) */
 } pamg_stats;
 
 void pamg_default_options(pamg_options* o);
@@ -171,7 +173,7 @@ int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double
  * handle blobs (torch.distributed / MPI.Allgather), nothing else crosses processes on the host. */
 int pamg_device_init(pamg_ctx* c, int32_t nlocal, const int32_t* local_parts,
                      const int32_t* device_ids);
-/* change the kernel-side knobs (spmv_format, lanes_per_row, use_graph, sell_*) of an existing hierarchy;
+/* change the kernel-side knobs (spmv_format, lanes_per_row, use_graph, sell_*, fuse_halo, tail_rows) of an existing hierarchy;
  * takes effect at the next pamg_device_init.  Numerical options are ignored. */
 int pamg_set_kernel_options(pamg_ctx* c, const pamg_options* o);
 int32_t pamg_comm_handle_bytes(void);

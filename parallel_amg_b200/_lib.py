@@ -46,7 +46,7 @@ class Stats(C.Structure):
         ("iters", C.c_int32), ("converged", C.c_int32), ("r0_norm", C.c_double), ("r_norm", C.c_double),
         ("solve_ms", C.c_double), ("vcycle_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("n_levels", C.c_int32), ("format", C.c_int32 * 16), ("lanes", C.c_int32 * 16),
-        ("format_p", C.c_int32 * 16), ("format_r", C.c_int32 * 16), ("sell_fill", C.c_double * 16), ("fused_halo", C.c_int32),
+        ("format_p", C.c_int32 * 16), ("format_r", C.c_int32 * 16), ("sell_fill", C.c_double * 16), ("fused_halo", C.c_int32), ("tail_level", C.c_int32),
     ]
 
 

@@ -145,7 +145,7 @@ void pamg_default_options(pamg_options* o) {
   o->spmv_format = PAMG_FORMAT_AUTO;
   o->use_graph = 1;
   o->lanes_per_row = 0;
-  o->tail_rows = 0;
+  o->tail_rows = 131072;
   o->sell_sigma = 0;
   o->sell_rows_per_thread = 0;
   o->fuse_halo = 1;
@@ -509,6 +509,7 @@ int pamg_set_kernel_options(pamg_ctx* c, const pamg_options* o) {
     c->h.opts.sell_sigma = o->sell_sigma;
     c->h.opts.sell_rows_per_thread = o->sell_rows_per_thread;
     c->h.opts.fuse_halo = o->fuse_halo;
+    c->h.opts.tail_rows = o->tail_rows;
     return PAMG_OK;
   });
 }

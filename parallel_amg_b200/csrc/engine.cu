@@ -173,13 +173,62 @@ void build_bnd(const LocalCsr& oo, const LocalCsr& og, DevBnd& d) {
       ptr.push_back((int32_t)col.size());
     }
   d.n = (int)rows.size();
-  d.lanes = std::min(32, std::max(2, pick_lanes(d.n ? (double)col.size() / d.n : 0.0)));
+  // latency-bound role: one thread per row up to 16 entries (all its loads are independent), wider above
+  const double mean = d.n ? (double)col.size() / d.n : 0.0;
+  d.lanes = mean <= 16 ? 1 : mean <= 32 ? 2 : mean <= 64 ? 4 : mean <= 128 ? 8 : mean <= 256 ? 16 : 32;
   d.rows.upload(rows);
   d.ptr.upload(ptr);
   d.mid.upload(mid);
   d.col.upload(col);
   d.val.upload(val);
   d.skip.upload(skip);
+}
+
+// Rows of all parts of one operator merged into one matrix in gid numbering (replicated coarse tail).
+// which: PAMG_A_OO (rows/cols level l), PAMG_P_OO (rows l, cols l+1), PAMG_R_OO (rows l+1, cols l).
+// A row keeps the order mul! sums it in: own-part columns, then ghost columns.
+void merged_block(const Hierarchy& h, int l, int which, LocalCsr& out) {
+  const int lr = which == PAMG_R_OO ? l + 1 : l;
+  const int lc = which == PAMG_P_OO ? l + 1 : l;
+  const int64_t nr = h.levels[lr].n_global, nc = h.levels[lc].n_global;
+  out = LocalCsr();
+  out.nrows = nr;
+  out.ncols = nc;
+  out.ptr.assign(nr + 1, 0);
+  for (int p = 0; p < h.nparts; ++p) {
+    const PartLevel& pl = h.levels[l].parts[p];
+    const PartLevel& pr = h.levels[lr].parts[p];
+    const LocalCsr &oo = pl.blk[which], &og = pl.blk[which + 1];
+    for (int64_t i = 0; i < pr.n_own; ++i) {
+      int64_t cnt = 0;
+      if (!oo.ptr.empty()) cnt += oo.ptr[i + 1] - oo.ptr[i];
+      if (!og.ptr.empty()) cnt += og.ptr[i + 1] - og.ptr[i];
+      out.ptr[pr.own_to_global[i] + 1] = cnt;
+    }
+  }
+  for (int64_t g = 0; g < nr; ++g) out.ptr[g + 1] += out.ptr[g];
+  if (out.ptr[nr] > INT32_MAX) throw std::runtime_error("merged tail level exceeds int32 entries (lower tail_rows)");
+  out.col.resize(out.ptr[nr]);
+  out.val.resize(out.ptr[nr]);
+  for (int p = 0; p < h.nparts; ++p) {
+    const PartLevel& pl = h.levels[l].parts[p];
+    const PartLevel& pr = h.levels[lr].parts[p];
+    const PartLevel& pc = h.levels[lc].parts[p];
+    const LocalCsr &oo = pl.blk[which], &og = pl.blk[which + 1];
+    for (int64_t i = 0; i < pr.n_own; ++i) {
+      int64_t q = out.ptr[pr.own_to_global[i]];
+      if (!oo.ptr.empty())
+        for (int64_t k = oo.ptr[i]; k < oo.ptr[i + 1]; ++k) {
+          out.col[q] = (int32_t)pc.own_to_global[oo.col[k]];
+          out.val[q++] = oo.val[k];
+        }
+      if (!og.ptr.empty())
+        for (int64_t k = og.ptr[i]; k < og.ptr[i + 1]; ++k) {
+          out.col[q] = (int32_t)pc.ghost_to_global[og.col[k]];
+          out.val[q++] = og.val[k];
+        }
+    }
+  }
 }
 
 // AUTO takes SELL-C-sigma when its padding stores at most this many entries per nonzero
@@ -312,6 +361,17 @@ struct ArenaLayout {
   size_t coarse = 0, coarse_flags = 0, red = 0, red_flags = 0, total = 0;
 };
 
+// First level of the replicated coarse tail: levels [tail, L) are merged over all parts and run by every
+// GPU alone (coarse-level agglomeration).  Decided from replicated metadata, so every process agrees.
+int tail_level_of(const Hierarchy& h) {
+  const int L = (int)h.levels.size();
+  if (L <= 1) return 0;
+  if (h.nparts == 1 || h.opts.tail_rows <= 0) return L - 1;
+  for (int l = 1; l < L; ++l)
+    if (h.levels[l].n_global <= h.opts.tail_rows) return l;
+  return L - 1;
+}
+
 ArenaLayout arena_layout(const Hierarchy& h, int part) {
   ArenaLayout a;
   size_t off = 0;
@@ -327,7 +387,7 @@ ArenaLayout arena_layout(const Hierarchy& h, int part) {
     a.asm_stage.push_back(take(pl.send_idx.size() * sizeof(double)));
     a.asm_flags.push_back(take(pl.send.size() * sizeof(uint32_t)));
   }
-  a.coarse = take(2 * (size_t)h.n_coarse * sizeof(double));
+  a.coarse = take(2 * (size_t)h.levels[tail_level_of(h)].n_global * sizeof(double));
   a.coarse_flags = take((size_t)h.nparts * sizeof(uint32_t));
   a.red = take(2 * (size_t)h.nparts * RED_W * sizeof(double));
   a.red_flags = take((size_t)h.nparts * sizeof(uint32_t));
@@ -365,6 +425,7 @@ struct PartDev {
   int part = -1, device = 0;
   cudaStream_t stream = nullptr;
   std::vector<std::unique_ptr<LevelDev>> lev;
+  std::vector<std::unique_ptr<LevelDev>> tlev;  // merged (replicated) levels [tail_level, L), null below
   ArenaLayout lay;
   char* arena = nullptr;
   DBuf<DevState> st;
@@ -373,7 +434,7 @@ struct PartDev {
   RedCtx rc{};
   DBuf<CoarsePub> coarse_pubs;
   DBuf<double> inv;
-  DBuf<int64_t> own_gid_L, ghost_gid_L;
+  DBuf<int64_t> own_gid_T, ghost_gid_T;
   DBuf<double> xsol, p, q, bsave, hist, scratch4;
   DBuf<double> io_local;  // own+ghost staging for consistent!/assemble!
   int hist_cap = 0;
@@ -383,6 +444,10 @@ struct PartDev {
 struct Engine::Impl {
   Hierarchy* h = nullptr;
   int nparts = 0, L = 0;
+  int tail_level = 0;      // levels >= tail_level run replicated (merged over all parts) on every GPU
+  bool tail_mode = false;  // enqueue_* address the merged levels
+  LevelDev& LV(PartDev& pd, int l) { return tail_mode ? *pd.tlev[l] : *pd.lev[l]; }
+  LevelDev& LV(size_t i, int l) { return LV(*parts[i], l); }
   std::vector<std::unique_ptr<PartDev>> parts;         // local parts
   std::vector<int> local_index;                        // part -> index in parts or -1
   std::vector<char*> arena_of;                         // part -> arena base as seen from this process
@@ -584,13 +649,14 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     need = I.need_halo_R[l];
   else
     need = I.need_halo_P[l];
+  if (I.tail_mode) need = false;  // merged levels: every column is an own column
   const bool exchange = need && !op.coarse_ghosts_local;
   const bool fused = I.fused_halo;
   const int wsel = op.which / 2;  // 0 A, 1 P, 2 R
 
   auto halo_args = [&](PartDev& pd, bool with_pack, bool with_bnd) {
-    LevelDev& ld = *pd.lev[l];
-    LevelDev& hl = *pd.lev[op.halo_level];
+    LevelDev& ld = I.LV(pd, l);
+    LevelDev& hl = I.LV(pd, op.halo_level);
     FusedHalo fh{};
     fh.level = op.halo_level;
     fh.fixed_parity = op.coarse_ghosts_local ? 0 : -1;
@@ -598,7 +664,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     fh.skip = need ? ld.bnd[wsel].skip.p : nullptr;
     if (ld.bnd[wsel].n == 0) fh.skip = nullptr;
     if (with_pack) {
-      fh.n_pack = std::max(1, std::min(32, (hl.n_send + BLOCK * 4 - 1) / (BLOCK * 4)));
+      fh.n_pack = std::max(1, std::min(2 * 148, (hl.n_send + BLOCK - 1) / BLOCK));  // one value per thread: no serial store chain
       fh.n_send = hl.n_send;
       fh.n_nbrs = hl.n_send_nbrs;
       fh.send_idx = hl.send_idx.p;
@@ -607,14 +673,14 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     if (with_bnd) {
       const DevBnd& b = ld.bnd[wsel];
       const int rpb = BLOCK / b.lanes;
-      fh.n_bnd = std::max(1, std::min(148, (b.n + rpb - 1) / rpb));
+      fh.n_bnd = std::max(1, std::min(4 * 148, (b.n + rpb - 1) / rpb));
       fh.B = b.view();
       fh.hr = hl.hr;
     }
     return fh;
   };
   auto launch_main = [&](PartDev& pd, size_t i, const FusedHalo& fh, int publish) {
-    LevelDev& ld = *pd.lev[l];
+    LevelDev& ld = I.LV(pd, l);
     const DevCsr& m = ld.blk[op.which];
     LaunchArgs L{0, op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
     L.fh.v = xin[i];
@@ -639,7 +705,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   if (fused) {  // one launch per part: pack + main + boundary roles
     for (size_t i = 0; i < I.parts.size(); ++i) {
       PartDev& pd = I.P(i);
-      LevelDev& hl = *pd.lev[op.halo_level];
+      LevelDev& hl = I.LV(pd, op.halo_level);
       const bool nbrs = hl.n_recv_nbrs > 0 || hl.n_send_nbrs > 0;
       I.set_dev(pd);
       const FusedHalo fh = halo_args(pd, exchange && nbrs, need && nbrs);
@@ -653,7 +719,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   if (exchange)
     for (size_t i = 0; i < I.parts.size(); ++i) {
       PartDev& pd = I.P(i);
-      LevelDev& hl = *pd.lev[op.halo_level];
+      LevelDev& hl = I.LV(pd, op.halo_level);
       if (hl.n_send_nbrs == 0 && hl.n_recv_nbrs == 0) continue;
       I.set_dev(pd);
       k_halo_pack<<<I.grid_for(hl.n_send, BLOCK * 4), BLOCK, 0, pd.stream>>>(xin[i], hl.send_idx.p, hl.n_send, hl.send_nbrs.p,
@@ -663,7 +729,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   // phase 2: all rows of the own-own block (boundary rows are computed but not stored)
   for (size_t i = 0; i < I.parts.size(); ++i) {
     PartDev& pd = I.P(i);
-    LevelDev& hl = *pd.lev[op.halo_level];
+    LevelDev& hl = I.LV(pd, op.halo_level);
     const bool bnd_follows = need && hl.n_recv_nbrs > 0;
     I.set_dev(pd);
     const FusedHalo fh = halo_args(pd, false, false);
@@ -673,7 +739,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   if (need)
     for (size_t i = 0; i < I.parts.size(); ++i) {
       PartDev& pd = I.P(i);
-      LevelDev& hl = *pd.lev[op.halo_level];
+      LevelDev& hl = I.LV(pd, op.halo_level);
       if (hl.n_recv_nbrs == 0) continue;
       I.set_dev(pd);
       const FusedHalo fh = halo_args(pd, false, true);
@@ -712,6 +778,37 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       if (pl.blk[PAMG_A_OG].nnz() > 0) I.need_halo_A[l] = 1;
       if (pl.blk[PAMG_R_OG].nnz() > 0) I.need_halo_R[l] = 1;
       if (pl.blk[PAMG_P_OG].nnz() > 0) I.need_halo_P[l] = 1;
+    }
+
+  I.tail_level = tail_level_of(*h);
+  // merged (replicated) tail levels: built once on the host, uploaded to every local part's device
+  std::vector<LocalCsr> tA(I.L), tP(I.L), tR(I.L);
+  std::vector<std::vector<double>> tw(I.L), tdinv(I.L);
+  if (I.tail_level < I.L - 1)
+    for (int l = I.tail_level; l < I.L; ++l) {
+      const int64_t n = h->levels[l].n_global;
+      merged_block(*h, l, PAMG_A_OO, tA[l]);
+      if (l + 1 < I.L) {
+        merged_block(*h, l, PAMG_P_OO, tP[l]);
+        merged_block(*h, l, PAMG_R_OO, tR[l]);
+      }
+      tw[l].assign(n, 0.0);
+      tdinv[l].assign(n, 0.0);
+      const double rho = h->levels[l].rho;
+      const double theta = 0.5 * (o.cheb_hi_frac * rho + o.cheb_lo_frac * rho);
+      for (int p = 0; p < I.nparts; ++p) {
+        const PartLevel& pl = h->levels[l].parts[p];
+        for (int64_t k = 0; k < pl.n_own; ++k) {
+          const int64_t g = pl.own_to_global[k];
+          tdinv[l][g] = 1.0 / pl.diag[k];
+          if (o.smoother == PAMG_SMOOTHER_L1JACOBI)
+            tw[l][g] = 1.0 / pl.diag_l1[k];
+          else if (o.smoother == PAMG_SMOOTHER_CHEBYSHEV)
+            tw[l][g] = (1.0 / theta) / pl.diag[k];
+          else
+            tw[l][g] = o.omega_jacobi / pl.diag[k];
+        }
+      }
     }
 
   for (int i = 0; i < nlocal; ++i) {
@@ -807,11 +904,37 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       }
     }
     pd.partials.alloc((size_t)max_blocks + 512);  // one partial per CTA of a fused-reduction kernel
-    // coarsest solve data
-    const PartLevel& pc = h->levels[I.L - 1].parts[part];
+    // replicated tail: merged levels + the maps of the level it is entered through
+    pd.tlev.resize(I.L);
+    if (I.tail_level < I.L - 1)
+      for (int l = I.tail_level; l < I.L; ++l) {
+        pd.tlev[l].reset(new LevelDev);
+        LevelDev& tl = *pd.tlev[l];
+        const int64_t n = h->levels[l].n_global;
+        tl.n_own = n;
+        tl.n_ghost = 0;
+        const LocalCsr empty;
+        build_csr(tA[l], false, tl.blk[PAMG_A_OO], 0, o.spmv_format, o, PAMG_A_OO);
+        build_csr(tP[l], false, tl.blk[PAMG_P_OO], 0, o.spmv_format, o, PAMG_P_OO);
+        build_csr(tR[l], false, tl.blk[PAMG_R_OO], 0, o.spmv_format, o, PAMG_R_OO);
+        for (int b = 0; b < 3; ++b) build_bnd(empty, empty, tl.bnd[b]);
+        tl.w.upload(tw[l]);
+        tl.dinv.upload(tdinv[l]);
+        tl.x.alloc(n);
+        tl.x2.alloc(n);
+        tl.b.alloc(n);
+        tl.t.alloc(n);
+        if (o.smoother == PAMG_SMOOTHER_CHEBYSHEV) {
+          tl.d.alloc(n);
+          tl.d2.alloc(n);
+        }
+        tl.send_idx.alloc(0);
+        tl.send_nbrs.alloc(0);
+      }
+    const PartLevel& pc = h->levels[I.tail_level].parts[part];
     pd.inv.upload(h->coarse_inv);
-    pd.own_gid_L.upload(pc.own_to_global);
-    pd.ghost_gid_L.upload(pc.ghost_to_global);
+    pd.own_gid_T.upload(pc.own_to_global);
+    pd.ghost_gid_T.upload(pc.ghost_to_global);
     // PCG vectors on level 0
     const int64_t n0 = h->levels[0].parts[part].n_own;
     pd.xsol.alloc(n0);
@@ -854,8 +977,11 @@ void Engine::plan_buffers() {
   int flips = 1;  // prolongation writes out of place
   if (o.nu_pre > 0) flips += o.nu_pre * steps - 1;  // the zero-guess first step is written by the producer of b
   flips += o.nu_post * steps;
-  for (auto& up : I.parts)
+  for (auto& up : I.parts) {
     for (auto& ld : up->lev) ld->xstart = (flips % 2 == 0) ? ld->x.p : ld->x2.p;
+    for (auto& ld : up->tlev)
+      if (ld) ld->xstart = (flips % 2 == 0) ? ld->x.p : ld->x2.p;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -964,7 +1090,7 @@ void Engine::connect() {
       rp[d].flag = (uint32_t*)(qa + lay[d].red_flags) + me;
       double* c0 = (double*)(qa + lay[d].coarse);
       cp[d].buf[0] = c0;
-      cp[d].buf[1] = c0 + h.n_coarse;
+      cp[d].buf[1] = c0 + h.levels[I.tail_level].n_global;
       cp[d].flag = (uint32_t*)(qa + lay[d].coarse_flags) + me;
     }
     pd.red_pubs.upload(rp);
@@ -1068,7 +1194,7 @@ void Engine::enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_
   const pamg_options& o = I.h->opts;
   const size_t np = I.parts.size();
   auto other = [&](size_t i) {
-    LevelDev& ld = *I.P(i).lev[l];
+    LevelDev& ld = I.LV(i, l);
     return cur[i] == ld.x.p ? ld.x2.p : ld.x.p;
   };
   if (o.smoother != PAMG_SMOOTHER_CHEBYSHEV) {
@@ -1078,7 +1204,7 @@ void Engine::enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_
       std::vector<double*> nxt(np);
       const bool dot = dot_last && s == nu - 1;
       for (size_t i = 0; i < np; ++i) {
-        LevelDev& ld = *I.P(i).lev[l];
+        LevelDev& ld = I.LV(i, l);
         nxt[i] = other(i);
         xin[i] = cur[i];
         epi[i] = EpiArgs{nxt[i], ld.b.p, cur[i], ld.w.p, nullptr, nullptr, dot ? ld.b.p : nullptr, 0.0, 0.0};
@@ -1115,7 +1241,7 @@ void Engine::enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_
       std::vector<double*> nxt(np);
       const bool dot = dot_last && s == nu - 1 && k == deg - 1;
       for (size_t i = 0; i < np; ++i) {
-        LevelDev& ld = *I.P(i).lev[l];
+        LevelDev& ld = I.LV(i, l);
         nxt[i] = other(i);
         xin[i] = cur[i];
         double* dnew = (dcur[i] == ld.d.p) ? ld.d2.p : ld.d.p;
@@ -1130,27 +1256,62 @@ void Engine::enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_
   }
 }
 
-void Engine::enqueue_coarse_solve() {
+// Levels [tail_level, L).  With only the coarsest level in the tail: all-gather b_L and apply the dense
+// inverse to this part's own + ghost rows.  Otherwise: all-gather b of the first tail level, run the
+// merged levels on this GPU alone (no halo), and scatter x back to this part's own + ghost slots.
+void Engine::enqueue_tail() {
   Impl& I = *impl;
-  const int l = I.L - 1;
-  const int n = (int)I.h->n_coarse;
+  const int l = I.tail_level;
+  const int n = (int)I.h->levels[l].n_global;
+  const pamg_options& o = I.h->opts;
   for (auto& up : I.parts) {
     PartDev& pd = *up;
     LevelDev& ld = *pd.lev[l];
     I.set_dev(pd);
-    k_coarse_gather<<<I.grid_for(ld.n_own, BLOCK), BLOCK, 0, pd.stream>>>(ld.b.p, pd.own_gid_L.p, (int)ld.n_own, pd.coarse_pubs.p,
+    k_coarse_gather<<<I.grid_for(ld.n_own, BLOCK), BLOCK, 0, pd.stream>>>(ld.b.p, pd.own_gid_T.p, (int)ld.n_own, pd.coarse_pubs.p,
                                                                          I.nparts, pd.st.p);
     I.note_launch();
   }
+  if (l == I.L - 1) {
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& ld = *pd.lev[l];
+      I.set_dev(pd);
+      const int rows = (int)(ld.n_own + ld.n_ghost);
+      const double* c0 = (const double*)(pd.arena + pd.lay.coarse);
+      k_coarse_solve<<<I.grid_for(std::max(rows, 1), BLOCK / 32), BLOCK, 0, pd.stream>>>(
+          pd.inv.p, n, c0, c0 + n, (const uint32_t*)(pd.arena + pd.lay.coarse_flags), I.nparts, pd.own_gid_T.p, (int)ld.n_own,
+          pd.ghost_gid_T.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
+      I.note_launch();
+    }
+    CK(cudaGetLastError());
+    return;
+  }
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    LevelDev& tl = *pd.tlev[l];
+    I.set_dev(pd);
+    const double* c0 = (const double*)(pd.arena + pd.lay.coarse);
+    k_tail_in<<<I.grid_for(n, BLOCK), BLOCK, 0, pd.stream>>>(c0, c0 + n, (const uint32_t*)(pd.arena + pd.lay.coarse_flags), I.nparts,
+                                                             tl.b.p, tl.xstart, o.nu_pre > 0 ? tl.w.p : nullptr, n, pd.st.p);
+    I.note_launch();
+  }
+  CK(cudaGetLastError());
+  I.tail_mode = true;
+  try {
+    enqueue_vcycle(l, false);
+  } catch (...) {
+    I.tail_mode = false;
+    throw;
+  }
+  I.tail_mode = false;
   for (auto& up : I.parts) {
     PartDev& pd = *up;
     LevelDev& ld = *pd.lev[l];
+    LevelDev& tl = *pd.tlev[l];
     I.set_dev(pd);
-    const int rows = (int)(ld.n_own + ld.n_ghost);
-    const double* c0 = (const double*)(pd.arena + pd.lay.coarse);
-    k_coarse_solve<<<I.grid_for(std::max(rows, 1), BLOCK / 32), BLOCK, 0, pd.stream>>>(
-        pd.inv.p, n, c0, c0 + n, (const uint32_t*)(pd.arena + pd.lay.coarse_flags), I.nparts, pd.own_gid_L.p, (int)ld.n_own,
-        pd.ghost_gid_L.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
+    k_tail_out<<<I.grid_for(std::max<int64_t>(ld.n_own + ld.n_ghost, 1), BLOCK), BLOCK, 0, pd.stream>>>(
+        tl.x.p, pd.own_gid_T.p, (int)ld.n_own, pd.ghost_gid_T.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
     I.note_launch();
   }
   CK(cudaGetLastError());
@@ -1162,19 +1323,33 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
   Impl& I = *impl;
   const pamg_options& o = I.h->opts;
   const size_t np = I.parts.size();
-  if (l == I.L - 1) {
-    enqueue_coarse_solve();
+  if (!I.tail_mode && l == I.tail_level) {
+    enqueue_tail();
     return;
   }
+  if (I.tail_mode && l == I.L - 1) {  // coarsest level of the replicated tail: x = A_L^-1 b, whole vector
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& ld = I.LV(pd, l);
+      I.set_dev(pd);
+      k_dense<<<I.grid_for(std::max<int64_t>(ld.n_own, 1), BLOCK / 32), BLOCK, 0, pd.stream>>>(pd.inv.p, (int)ld.n_own, ld.b.p, ld.x.p,
+                                                                                             pd.st.p);
+      I.note_launch();
+    }
+    CK(cudaGetLastError());
+    return;
+  }
+  // the next level is entered through the tail gather / the dense solve: no fused zero-guess step for it
+  const bool next_is_entry = I.tail_mode ? (l + 1 == I.L - 1) : (l + 1 == I.tail_level);
   std::vector<double*> cur(np);
-  for (size_t i = 0; i < np; ++i) cur[i] = I.P(i).lev[l]->xstart;
+  for (size_t i = 0; i < np; ++i) cur[i] = I.LV(i, l).xstart;
   if (o.nu_pre > 0) enqueue_smooth(l, o.nu_pre, cur, /*zero_guess_done=*/true, false);
   // residual t = b - A x
   {
     std::vector<EpiArgs> epi(np);
     std::vector<const double*> xin(np);
     for (size_t i = 0; i < np; ++i) {
-      LevelDev& ld = *I.P(i).lev[l];
+      LevelDev& ld = I.LV(i, l);
       xin[i] = cur[i];
       epi[i] = EpiArgs{ld.t.p, ld.b.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
     }
@@ -1183,12 +1358,12 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
   }
   // restriction b_c = R t, fused with the coarse level's zero-guess first smoothing step
   {
-    const bool coarse_is_last = (l + 1 == I.L - 1);
+    const bool coarse_is_last = next_is_entry;
     std::vector<EpiArgs> epi(np);
     std::vector<const double*> xin(np);
     for (size_t i = 0; i < np; ++i) {
-      LevelDev& ld = *I.P(i).lev[l];
-      LevelDev& lc = *I.P(i).lev[l + 1];
+      LevelDev& ld = I.LV(i, l);
+      LevelDev& lc = I.LV(i, l + 1);
       xin[i] = ld.t.p;
       double* out2 = coarse_is_last ? nullptr : lc.xstart;
       const double* w = (o.nu_pre > 0) ? lc.w.p : nullptr;
@@ -1200,7 +1375,7 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
     if (!coarse_is_last && o.nu_pre == 0)
       for (size_t i = 0; i < np; ++i) {
         PartDev& pd = I.P(i);
-        LevelDev& lc = *pd.lev[l + 1];
+        LevelDev& lc = I.LV(pd, l + 1);
         I.set_dev(pd);
         k_scale<<<I.grid_for(lc.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(lc.b.p, nullptr, lc.xstart, (int)lc.n_own, pd.st.p);
         I.note_launch();
@@ -1213,19 +1388,19 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
     std::vector<const double*> xin(np);
     std::vector<double*> nxt(np);
     for (size_t i = 0; i < np; ++i) {
-      LevelDev& ld = *I.P(i).lev[l];
-      LevelDev& lc = *I.P(i).lev[l + 1];
+      LevelDev& ld = I.LV(i, l);
+      LevelDev& lc = I.LV(i, l + 1);
       nxt[i] = (cur[i] == ld.x.p) ? ld.x2.p : ld.x.p;
       xin[i] = lc.x.p;
       epi[i] = EpiArgs{nxt[i], cur[i], nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
     }
-    OpSpec op{l, PAMG_P_OO, l + 1, M_ADD, false, 0, (l + 1 == I.L - 1)};
+    OpSpec op{l, PAMG_P_OO, l + 1, M_ADD, false, 0, !I.tail_mode && l + 1 == I.tail_level};
     enqueue_op(op, xin, epi);
     cur = nxt;
   }
   if (o.nu_post > 0) enqueue_smooth(l, o.nu_post, cur, false, dot_rz);
   for (size_t i = 0; i < np; ++i)
-    if (cur[i] != I.P(i).lev[l]->x.p) throw std::runtime_error("internal: V-cycle buffer plan mismatch");
+    if (cur[i] != I.LV(i, l).x.p) throw std::runtime_error("internal: V-cycle buffer plan mismatch");
 }
 
 // r.z when the V-cycle could not fuse it (nu_post == 0, Chebyshev, or a single-level hierarchy)
@@ -1776,6 +1951,7 @@ void Engine::get_stats(pamg_stats* s) {
   *s = I.stats;
   s->n_levels = I.L;
   s->fused_halo = I.fused_halo ? 1 : 0;
+  s->tail_level = I.tail_level;
   auto fmt_of = [](const DevCsr& m) { return m.sell_rpt ? PAMG_FORMAT_SELL : m.stream ? PAMG_FORMAT_STREAM : PAMG_FORMAT_CSR; };
   for (int l = 0; l < 16; ++l) {
     const bool have = l < I.L && !I.parts.empty();

@@ -69,7 +69,7 @@ class Engine {
   void clear_done();
   void enqueue_op(const OpSpec& op, const std::vector<const double*>& xin, const std::vector<EpiArgs>& epi);
   void enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_guess_done, bool dot_last);
-  void enqueue_coarse_solve();
+  void enqueue_tail();
   void enqueue_vcycle(int l, bool dot_rz);
   void enqueue_vcycle_entry();
   void enqueue_dot_rz();

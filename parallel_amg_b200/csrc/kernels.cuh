@@ -12,12 +12,12 @@
 //   pack CTAs     (lowest block ids)  store this part's boundary values straight into the neighbour
 //                                     GPUs' ghost staging over NVLink peer mappings, then publish an
 //                                     epoch flag (release, system scope);
+//   boundary CTAs (next block ids)    spin on the local flags (acquire), then compute the boundary rows
+//                                     completely: own columns, then ghost columns, then the epilogue.
+//                                     They are few, latency-bound and dispatched early, so both the NVLink
+//                                     latency and their own run behind the main role's streaming;
 //   main CTAs                         all rows of the own-own block; rows that also have ghost columns
-//                                     ("boundary rows", marked in `skip`) are computed but not stored;
-//   boundary CTAs (highest block ids) spin on the local flags (acquire) -- by the time they are
-//                                     dispatched the interior work has hidden the NVLink latency --
-//                                     and compute the boundary rows completely: own columns then
-//                                     ghost columns, then the epilogue.
+//                                     ("boundary rows", marked in `skip`) are computed but not stored.
 // Staging buffers are double-buffered by epoch parity; see DESIGN.md "Halo protocol" for why that
 // is race-free.  When several parts share one GPU (the PartitionedArrays "debug backend" layout
 // used by the single-GPU tests) a kernel must never wait for a later kernel of the same stream, so
@@ -362,11 +362,18 @@ __device__ __forceinline__ double boundary_role(const FusedHalo& fh, const doubl
       end = B.ptr[k + 1];
     }
     double s = 0.0, sg = 0.0;
-    for (int q = beg + lane; q < mid; q += lanes) s += ldg_stream(B.val + q) * x[ldg_stream(B.col + q)];
-    for (int q = mid + lane; q < end; q += lanes) sg += ldg_stream(B.val + q) * __ldcv(g + ldg_stream(B.col + q));
-    for (int o = lanes >> 1; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    if (lanes == 1) {  // short rows: one thread per row, unit stride so that the loads are batched
+#pragma unroll 4
+      for (int q = beg; q < mid; ++q) s += ldg_stream(B.val + q) * x[ldg_stream(B.col + q)];
+#pragma unroll 4
+      for (int q = mid; q < end; ++q) sg += ldg_stream(B.val + q) * __ldcv(g + ldg_stream(B.col + q));
+    } else {
+      for (int q = beg + lane; q < mid; q += lanes) s += ldg_stream(B.val + q) * x[ldg_stream(B.col + q)];
+      for (int q = mid + lane; q < end; q += lanes) sg += ldg_stream(B.val + q) * __ldcv(g + ldg_stream(B.col + q));
+      for (int o = lanes >> 1; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      }
     }
     if (valid && lane == 0) {
       const int row = B.rows[k];
@@ -396,10 +403,10 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
   if (bid < fh.n_pack) {
     pack_role(fh, st, bid);
-  } else if (bid >= fh.n_pack + n_main) {
-    acc = boundary_role<MODE, DOT>(fh, x, a, st, bid - fh.n_pack - n_main);
+  } else if (bid < fh.n_pack + fh.n_bnd) {
+    acc = boundary_role<MODE, DOT>(fh, x, a, st, bid - fh.n_pack);
   } else {
-    bid -= fh.n_pack;
+    bid -= fh.n_pack + fh.n_bnd;
     constexpr int RPB = BLOCK / LANES;
     const int lane = threadIdx.x % LANES;
     const int grp = threadIdx.x / LANES;
@@ -409,9 +416,11 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
       const int r = r0 + grp;
       const bool valid = r < A.nrows;
       int beg = 0, end = 0;
+      unsigned char sk = 0;
       if (valid) {
         beg = A.ptr[r];
         end = A.ptr[r + 1];
+        if (fh.skip) sk = fh.skip[r];
       }
       double s = 0.0;
       for (int k = beg + lane; k < end; k += LANES) {
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
         s += v * x[c];
       }
       s = group_sum<LANES>(s);
-      if (valid && lane == 0 && !(fh.skip && fh.skip[r])) {
+      if (valid && lane == 0 && !sk) {
         const double res = apply_epilogue<MODE>(a, r, s);
         if (DOT) acc += a.dotv[r] * res;
       }
@@ -478,12 +487,12 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
   const int t = threadIdx.x;
   double acc = 0.0;
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
-  int bk0 = (int)blockIdx.x - fh.n_pack;
+  int bk0 = (int)blockIdx.x - fh.n_pack - fh.n_bnd;
   if ((int)blockIdx.x < fh.n_pack) {
     pack_role(fh, st, blockIdx.x);
     bk0 = A.nblocks;  // no main work
-  } else if (bk0 >= n_main) {
-    acc = boundary_role<MODE, DOT>(fh, x, a, st, bk0 - n_main);
+  } else if (bk0 < 0) {
+    acc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - fh.n_pack);
     bk0 = A.nblocks;
   }
   for (int bk = bk0; bk < A.nblocks; bk += n_main) {
@@ -493,11 +502,13 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
     const int n4 = (b1.y - ea + 3) >> 2;   // 4-entry groups to stream (<= S_STEPS * BLOCK by construction)
     // prefetch row extents and the first chunk's epilogue operands; their latency overlaps phase A
     int pb = 0, pe = 0;
+    unsigned char sk = 0;
     double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0, e_dot = 0.0;
     if (t < nr) {
       const int row = r0 + t;
       pb = A.ptr[row] - ea;
       pe = A.ptr[row + 1] - ea;
+      if (fh.skip) sk = fh.skip[row];
       if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
       if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
       if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
@@ -543,6 +554,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
         if (q > 0) {  // extents / operands of the later chunks (short-row matrices only) are fetched here
           pb = A.ptr[row] - ea;
           pe = A.ptr[row + 1] - ea;
+          if (fh.skip) sk = fh.skip[row];
           if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
           if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
           if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
         }
         double s = 0.0;
         for (int k = pb; k < pe; ++k) s += prod[k];
-        if (!(fh.skip && fh.skip[row])) {
+        if (!sk) {
           const double res = stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
           if (DOT) acc += e_dot * res;
         }
@@ -604,13 +616,13 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
                                                       FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
-  const int bid = (int)blockIdx.x - fh.n_pack;
-  if (bid < 0 || bid >= n_main) {  // halo roles
+  const int bid = (int)blockIdx.x - fh.n_pack - fh.n_bnd;
+  if (bid < 0) {  // halo roles
     double racc = 0.0;
-    if (bid < 0)
+    if ((int)blockIdx.x < fh.n_pack)
       pack_role(fh, st, blockIdx.x);
     else
-      racc = boundary_role<MODE, DOT>(fh, x, a, st, bid - n_main);
+      racc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - fh.n_pack);
     if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
     return;
   }
@@ -625,15 +637,17 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
     const int slot0 = sl * (32 * RPT) + lane * RPT;
     int row[RPT];
     double s[RPT];
+    unsigned char sk[RPT];  // requested before the entries are streamed, tested only in the epilogue
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       const int slot = slot0 + k;
       row[k] = -1;
       s[k] = 0.0;
+      sk[k] = 0;
       if (slot < A.nrows) {
         const int r = A.perm ? A.perm[slot] : slot;
-        if (fh.skip && fh.skip[r]) continue;
         row[k] = r;
+        if (fh.skip) sk[k] = fh.skip[r];
         if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) prefetch_l1(a.in0 + r);
         if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) prefetch_l1(a.w + r);
         if (MODE == M_CHEB && a.aux) prefetch_l1(a.aux + r);
@@ -667,7 +681,7 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
     }
 #pragma unroll
     for (int k = 0; k < RPT; ++k)
-      if (row[k] >= 0) {
+      if (row[k] >= 0 && !sk[k]) {
         const double res = apply_epilogue<MODE>(a, row[k], s[k]);
         if (DOT) acc += a.dotv[row[k]] * res;
       }
@@ -797,6 +811,62 @@ __global__ void __launch_bounds__(BLOCK) k_coarse_solve(const double* __restrict
       else
         xg[r - n_own] = s;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// replicated coarse tail (coarse-level agglomeration): below a size threshold every GPU holds the
+// whole level (all parts merged, gid numbering) and runs it alone, with no halo at all.
+//   k_coarse_gather : every part stores its slice of b into every part's gather buffer (+ flag)
+//   k_tail_in       : wait for all slices; b_full <- gather buffer; first zero-guess smoothing step
+//   ... the ordinary SpMV-family kernels on the merged matrices, k_dense on the coarsest level ...
+//   k_tail_out      : x_full -> this part's own slice and ghost staging (prolongation to the last
+//                     distributed level needs no exchange)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_tail_in(const double* g0, const double* g1, const uint32_t* flags, int nparts,
+                                                    double* __restrict__ b, double* __restrict__ xstart,
+                                                    const double* __restrict__ w, int n, DevState* st) {
+  if (st->done) return;
+  __shared__ int s_par;
+  if (threadIdx.x == 0) {
+    const uint32_t e = *(volatile uint32_t*)&st->coarse_epoch;
+    for (int d = 0; d < nparts; ++d) spin_until(flags + d, e, st);
+    s_par = (int)(e & 1u);
+  }
+  __syncthreads();
+  const double* g = s_par ? g1 : g0;
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+    const double v = __ldcv(g + i);
+    b[i] = v;
+    if (xstart) xstart[i] = w ? w[i] * v : 0.0;
+  }
+}
+
+// x = inv * b, one warp per row (coarsest level of the replicated tail)
+__global__ void __launch_bounds__(BLOCK) k_dense(const double* __restrict__ inv, int n, const double* __restrict__ b,
+                                                  double* __restrict__ x, DevState* st) {
+  if (st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * BLOCK) >> 5;
+  for (int r = warp; r < n; r += nwarps) {
+    const double* row = inv + (size_t)r * n;
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32) s += row[j] * b[j];
+    s = group_sum<32>(s);
+    if (lane == 0) x[r] = s;
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_tail_out(const double* __restrict__ xfull, const int64_t* __restrict__ own_gid, int n_own,
+                                                     const int64_t* __restrict__ ghost_gid, int n_ghost, double* __restrict__ x,
+                                                     double* __restrict__ xg, DevState* st) {
+  if (st->done) return;
+  for (int r = blockIdx.x * BLOCK + threadIdx.x; r < n_own + n_ghost; r += gridDim.x * BLOCK) {
+    if (r < n_own)
+      x[r] = xfull[own_gid[r]];
+    else
+      xg[r - n_own] = xfull[ghost_gid[r - n_own]];
   }
 }
 

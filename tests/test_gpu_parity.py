@@ -182,6 +182,26 @@ def test_pcg_iteration_count_and_history(dims, pp, oopts):
         assert np.linalg.norm(b - A @ xg) <= 1.0001e-8 * np.linalg.norm(b)
 
 
+@pytest.mark.parametrize("dims,pp", PROBLEMS[1:])
+@pytest.mark.parametrize("tail_rows", [0, 600, 1 << 20])
+def test_coarse_agglomeration_thresholds(dims, pp, tail_rows):
+    """Coarse-level agglomeration (levels merged over all parts and run replicated, pamg_options.tail_rows)
+    is an execution layout, not a different hierarchy: whatever the threshold, the V-cycle matches the
+    oracle's N-part V-cycle to 1e-12 and PCG takes the same number of iterations."""
+    A, h, c = make(dims, pp, None, tail_rows=tail_rows)
+    L_ = len(h["levels"])
+    sizes = [h["global"]["levels"][l]["A"].shape[0] for l in range(L_)]
+    want = L_ - 1 if tail_rows == 0 else next((l for l in range(1, L_) if sizes[l] <= tail_rows), L_ - 1)
+    assert c.stats().tail_level == want
+    lev = h["levels"][0]
+    b = det_vector(A.shape[0], 77)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, b))
+    x, it, hist, ok = c.pcg(own_parts(lev, b))
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
+
+
 def test_pcg_graph_and_eager_agree_bitwise():
     A, h, c1 = make((20, 20, 20), (2, 2, 2), None, use_graph=1)
     _, _, c0 = make((20, 20, 20), (2, 2, 2), None, use_graph=0)
