@@ -411,8 +411,9 @@ class Context:
         self._ck(self.lib.pamg_vcycle(self._h, bp, xp))
         return x
 
-    def pcg(self, b, rtol=1e-8, maxiter=200, precond=True):
-        x = self._new_own(0)
+    def pcg(self, b, rtol=1e-8, maxiter=200, precond=True, out=None):
+        """out: optional list of preallocated (e.g. pinned) float64 arrays receiving the own values of x."""
+        x = out if out is not None else self._new_own(0)
         bp, k1 = self._vecs(b)
         xp, k2 = self._vecs(x, writable=True)
         it = C.c_int32()
