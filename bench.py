@@ -139,6 +139,29 @@ def cpu_solve_timed(c, nparts, b_parts, reps):
     return times, it, hist
 
 
+def write_trace(c, part, path):
+    """Per-kernel timeline of one resident solve: start-to-start deltas (device globaltimer) of every kernel
+    of a PCG iteration, median over the iterations.  Diagnostic only (not part of any reported number)."""
+    c.trace_enable(1 << 16)
+    it, hist, ok = c.pcg_resident(RTOL, MAXITER, True)
+    t = c.trace_read(part).astype(np.int64)
+    c.trace_enable(0)
+    names = c.trace_names()
+    k = len(names)
+    body = t[2:]                       # k_pcg_init, k_check, then `it` iterations of k kernels
+    nit = min(it, len(body) // k) if k else 0
+    with open(path, "w") as fh:
+        fh.write(f"# iterations {it}, kernels per iteration {k}, records {len(t)}\n")
+        if nit < 2:
+            return
+        d = np.diff(body[: nit * k + 1].astype(np.float64))[: (nit - 1) * k + k - 1]
+        d = np.concatenate([d, [np.nan] * (nit * k - len(d))]).reshape(nit, k)
+        med = np.nanmedian(d, axis=0) / 1e3
+        fh.write(f"# median start-to-start delta per kernel (us); sum = {np.nansum(med):.1f} us per iteration\n")
+        for nm, m in zip(names, med):
+            fh.write(f"{m:9.2f}  {nm}\n")
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: there is no reference code to run and no Julia; the arm times
     the CPU oracle port (oracle/pamg_oracle.c) with all host threads on the same config."""
@@ -182,6 +205,7 @@ def main():
     ap.add_argument("--workload", default="poisson3d-256", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--smoother", default="jacobi")
+    ap.add_argument("--trace", default=None, help="write a per-kernel timeline of one solve (device globaltimer) to this file prefix")
     args = ap.parse_args()
     if args.gpus not in PARTS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
@@ -289,6 +313,9 @@ def main():
     assert true_rel <= 2e-8, f"true residual {true_rel}"
     sol_err = float(np.abs(xg - xs_true).max())
 
+    if args.trace:
+        write_trace(c, mine[0], args.trace + f".rank{rank}.txt")
+
     # ---- e2e: the C-ABI call with host buffers (H2D b, D2H x inside the timed region) ---------
     for _ in range(2):
         c.pcg(b_parts, RTOL, MAXITER, True, out=x_parts)
@@ -311,8 +338,9 @@ def main():
         ms = c.time_kernel(kind, 0, 13, True)[3:]
         kern[name] = dict(ms=float(np.mean(ms)), gbs=nbytes / (float(np.mean(ms)) * 1e-3) / 1e9, bytes=int(nbytes))
     stt = c.stats()
-    kname = ("k_spmv_stream<MUL> (CSR-stream, 128-bit coalesced loads, smem-staged products)" if stt.format[0] == L.FORMAT_STREAM
-             else f"k_spmv<lanes={stt.lanes[0]},MUL> (sub-warp CSR)")
+    kname = {L.FORMAT_SELL: "k_spmv_sell<RPT=2,MUL> (SELL-C-sigma, C=64, 128-bit value loads, persistent CTAs)",
+             L.FORMAT_STREAM: "k_spmv_stream<MUL> (CSR-stream, 128-bit coalesced loads, smem-staged products)"}.get(
+                 stt.format[0], f"k_spmv<lanes={stt.lanes[0]},MUL> (sub-warp CSR)")
 
     if world > 1:
         t = torch.tensor([dev_ms, wall_ms, e2e_ms], device="cuda", dtype=torch.float64)

@@ -212,10 +212,18 @@ int pamg_pcg_resident(pamg_ctx* c, double rtol, int32_t maxiter, int32_t precond
 int pamg_read_solution(pamg_ctx* c, double* const* x);
 /* time `reps` launches of one level-`level` kernel with CUDA events on the launching stream,
  * L2 flushed before each when flush_l2 != 0.  kind: 0 spmv, 1 smoother sweep,
- * 2 residual+restrict, 3 prolong+correct, 4 dot, 5 whole V-cycle.  ms_out[reps]. */
+ * 2 residual+restrict, 3 prolong+correct, 4 dot, 5 whole V-cycle, 6 spmv + fused dot, 7 smoother sweep + fused dot,
+ * 8 reference stream (read + write of a 256 MiB buffer; needs flush_l2).
+ * ms_out[reps]. */
 int pamg_time_kernel(pamg_ctx* c, int32_t kind, int32_t level, int32_t reps, int32_t flush_l2,
                      float* ms_out);
 int pamg_get_stats(pamg_ctx* c, pamg_stats* s);
+/* tracing: after pamg_trace_enable(capacity > 0) CTA 0 of every kernel launched for a local part appends its
+ * start time (device globaltimer, ns); pamg_trace_read copies and clears the record of one local part;
+ * pamg_trace_names returns the newline-separated kernel names of one PCG iteration in launch order. */
+int pamg_trace_enable(pamg_ctx* c, int32_t capacity);
+int pamg_trace_read(pamg_ctx* c, int32_t part, uint64_t* out, int32_t cap, int32_t* n);
+int pamg_trace_names(pamg_ctx* c, char* buf, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,9 @@ PROTOTYPES = {
     "pamg_read_solution": [_ctx, _vecs],
     "pamg_time_kernel": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(C.c_float)],
     "pamg_get_stats": [_ctx, _P(Stats)],
+    "pamg_trace_enable": [_ctx, C.c_int32],
+    "pamg_trace_read": [_ctx, C.c_int32, _P(C.c_uint64), C.c_int32, _i32p],
+    "pamg_trace_names": [_ctx, C.c_char_p, C.c_int32],
 }
 _RESTYPE = {"pamg_set_num_threads": None, "pamg_default_options": None, "pamg_destroy": None, "pamg_last_error": C.c_char_p,
             "pamg_comm_handle_bytes": C.c_int32}
@@ -443,6 +446,20 @@ class Context:
         ms = np.zeros(reps, np.float32)
         self._ck(self.lib.pamg_time_kernel(self._h, kind, level, reps, int(flush_l2), _ptr(ms, C.c_float)))
         return ms
+
+    def trace_enable(self, capacity=1 << 16):
+        self._ck(self.lib.pamg_trace_enable(self._h, int(capacity)))
+
+    def trace_read(self, part, cap=1 << 16):
+        out = np.zeros(cap, np.uint64)
+        n = C.c_int32()
+        self._ck(self.lib.pamg_trace_read(self._h, int(part), _ptr(out, C.c_uint64), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def trace_names(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.pamg_trace_names(self._h, buf, len(buf)))
+        return [s for s in buf.value.decode().split("\n") if s]
 
     def stats(self):
         s = Stats()

@@ -22,6 +22,7 @@ DEPS = ["host.hpp", "engine.hpp", "kernels.cuh", os.path.join("..", "..", "inclu
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-Xptxas", "-v"]
+NVCC_FLAGS += os.environ.get("PAMG_EXTRA_NVCC_FLAGS", "").split()  # experiments only (A/B builds under _ab/)
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall"]
 
 

@@ -628,6 +628,29 @@ int pamg_time_kernel(pamg_ctx* c, int32_t kind, int32_t level, int32_t reps, int
     return PAMG_OK;
   });
 }
+int pamg_trace_enable(pamg_ctx* c, int32_t capacity) {
+  return guard(c, [&] {
+    engine(c).trace_enable(capacity);
+    return PAMG_OK;
+  });
+}
+int pamg_trace_read(pamg_ctx* c, int32_t part, uint64_t* out, int32_t cap, int32_t* n) {
+  return guard(c, [&] {
+    need(out && n, "null output");
+    *n = engine(c).trace_read(part, (unsigned long long*)out, cap);
+    return PAMG_OK;
+  });
+}
+int pamg_trace_names(pamg_ctx* c, char* buf, int32_t cap) {
+  return guard(c, [&] {
+    need(buf && cap > 0, "null buffer");
+    const std::string s = engine(c).trace_names();
+    std::strncpy(buf, s.c_str(), (size_t)cap - 1);
+    buf[cap - 1] = 0;
+    return PAMG_OK;
+  });
+}
+
 int pamg_get_stats(pamg_ctx* c, pamg_stats* s) {
   return guard(c, [&] {
     need(s != nullptr, "null stats");

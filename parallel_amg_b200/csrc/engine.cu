@@ -7,6 +7,7 @@
 // live in the vectors: they arrive in a per-level, double-buffered staging area inside the
 // part's peer-visible "arena", written directly by the neighbouring GPUs.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -235,7 +236,7 @@ void merged_block(const Hierarchy& h, int l, int which, LocalCsr& out) {
 constexpr double SELL_AUTO_MAX_FILL = 1.25;
 // AUTO per operator (gpurun kernel sweep, profiles/r01_kernel_sweep.md): A -> SELL (0.29 vs 0.36 ms at 256^3);
 // R -> SELL only with enough coarse rows to fill the GPU one thread per row, else CSR-stream (few, long rows);
-// P (1-8 entries per row) -> CSR-stream, which ties SELL without needing a row permutation.
+// P (1-8 entries per row) -> SELL like A once the short-row kernels run as persistent CTAs (0.228 vs 0.268 ms).
 // (one thread per row needs >= ~200k rows to fill 148 SMs: at 44k rows x 68 nnz the SELL sweep takes 63 us, CSR-stream 20 us)
 constexpr int64_t SELL_AUTO_MIN_ROWS_A = 200000, SELL_AUTO_MIN_ROWS_R = 65536;
 
@@ -287,7 +288,7 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
   // ---- SELL-C-sigma ----
   bool auto_sell = false;
   if (fmt == PAMG_FORMAT_AUTO) {
-    if (which == PAMG_A_OO) auto_sell = nr >= SELL_AUTO_MIN_ROWS_A;
+    if (which == PAMG_A_OO || which == PAMG_P_OO) auto_sell = nr >= SELL_AUTO_MIN_ROWS_A;
     if (which == PAMG_R_OO) auto_sell = nr >= SELL_AUTO_MIN_ROWS_R;
   }
   if (!compress && nr > 0 && (fmt == PAMG_FORMAT_SELL || auto_sell)) {
@@ -296,7 +297,9 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     SellHost sh;
     int sigma = o.sell_sigma > 0 ? o.sell_sigma : 1;
     sell_layout(m, C, sigma, sh, false);
-    if (o.sell_sigma <= 0 && sh.fill > 1.05) {  // auto sigma: sort inside windows only when it pays
+    // auto sigma: sort inside windows only when the unsorted padding is large (the permutation costs more than
+    // ~20 % padding does: P at 256^3 runs 0.228 ms unsorted with 1.16x fill, 0.240 ms sorted with 1.01x)
+    if (o.sell_sigma <= 0 && sh.fill > 1.25) {
       SellHost s2;
       sell_layout(m, C, 64 * C, s2, false);
       if (s2.fill < sh.fill - 0.02) sigma = 64 * C;
@@ -430,6 +433,7 @@ struct PartDev {
   char* arena = nullptr;
   DBuf<DevState> st;
   DBuf<double> partials;
+  int partials_cap = 0;
   DBuf<RedPub> red_pubs;
   RedCtx rc{};
   DBuf<CoarsePub> coarse_pubs;
@@ -437,6 +441,7 @@ struct PartDev {
   DBuf<int64_t> own_gid_T, ghost_gid_T;
   DBuf<double> xsol, p, q, bsave, hist, scratch4;
   DBuf<double> io_local;  // own+ghost staging for consistent!/assemble!
+  DBuf<unsigned long long> trace;
   int hist_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -456,6 +461,7 @@ struct Engine::Impl {
   std::vector<void*> ipc_opened;
   std::map<int, cudaStream_t> stream_of_device;
   bool connected = false;
+  bool persistent = true;   // SELL / CSR-stream main roles run as one resident wave (env PAMG_PERSISTENT=0: one CTA per work item)
   bool fused_halo = false;  // every local part has a GPU of its own: halo roles run inside the consuming kernel
   int64_t launches = 0;
   bool counting = true;
@@ -469,9 +475,7 @@ struct Engine::Impl {
   double* flush_buf = nullptr;
   size_t flush_n = 0;
   pamg_stats stats{};
-  DevState* pinned = nullptr;  // ring of status snapshots
-  static constexpr int RING = 8;
-  cudaEvent_t ring_ev[RING]{};
+  HostStat* hstat = nullptr;  // pinned, device-mapped ring written by k_check of the first local part
   bool rhs_loaded = false;
 
   ~Impl();
@@ -488,17 +492,18 @@ struct Engine::Impl {
   int grid_red(int64_t work_items) const {
     return (int)std::max<int64_t>(1, std::min<int64_t>((work_items + BLOCK - 1) / BLOCK, RED_GRID));
   }
-  void note_launch() {
+  std::vector<std::string> names;  // kernel names in launch order while `naming` (graph capture of one PCG iteration)
+  bool naming = false;
+  void note_launch(const char* name = "kernel") {
     if (counting) ++launches;
+    if (naming) names.push_back(name);
   }
 };
 
 Engine::Impl::~Impl() {
   for (auto g : g_iter) cudaGraphExecDestroy(g);
   for (auto g : g_vcycle) cudaGraphExecDestroy(g);
-  for (int k = 0; k < RING; ++k)
-    if (ring_ev[k]) cudaEventDestroy(ring_ev[k]);
-  if (pinned) cudaFreeHost(pinned);
+  if (hstat) cudaFreeHost(hstat);
   for (auto& up : parts) {
     cudaSetDevice(up->device);
     if (up->ev0) cudaEventDestroy(up->ev0);
@@ -546,7 +551,7 @@ struct LaunchArgs {  // what every SpMV-family launch shares
   FusedHalo fh;
   double* partials;
   RedCtx rc;
-  int publish, slot;
+  int publish, slot;   // fused dot: publish = 1 total goes to every part, 0 a boundary launch completes it
 };
 
 int main_grid(const LaunchArgs& L, const void* kernel) {
@@ -682,7 +687,12 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   auto launch_main = [&](PartDev& pd, size_t i, const FusedHalo& fh, int publish) {
     LevelDev& ld = I.LV(pd, l);
     const DevCsr& m = ld.blk[op.which];
-    LaunchArgs L{0, op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
+    // persistent main role: one resident wave of CTAs striding over the slices / row blocks.  Measured on
+    // B200 (256^3): SELL Jacobi sweep 0.316 ms persistent vs 0.344 ms with one CTA per 8 slices.
+    // Long rows (level >= 1, 30+ entries per row) lose 10 % that way: they keep one CTA per 8 slices.
+    const double mean_nnz = m.nrows ? (double)m.nnz / m.nrows : 0.0;
+    const bool bounded = I.persistent && m.sell_rpt && mean_nnz <= 12.0;
+    LaunchArgs L{0, bounded || op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
     L.fh.v = xin[i];
     int n_main;
     if (m.sell_rpt) {
@@ -699,7 +709,18 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
       launch_stream(op.mode, op.dot, m.sview(), L);
     else
       launch_csr(op.mode, op.dot, m.lanes, m.view(), L);
-    I.note_launch();
+    if (I.naming) {
+      static const char* MODES[] = {"mul", "resid", "jacobi", "add", "restrict", "cheb"};
+      static const char* OPS[] = {"A", "P", "R"};
+      I.names.push_back(std::string(m.sell_rpt ? "sell " : m.stream ? "stream " : "csr ") + MODES[op.mode] + (op.dot ? "+dot " : " ") +
+                        OPS[wsel] + std::to_string(l) + (I.tail_mode ? " tail" : "") + (fh.n_pack ? " +pack" : "") +
+                        (fh.n_bnd ? " +bnd" : ""));
+      I.naming = false;
+      I.note_launch();
+      I.naming = true;
+    } else {
+      I.note_launch();
+    }
   };
 
   if (fused) {  // one launch per part: pack + main + boundary roles
@@ -724,7 +745,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
       I.set_dev(pd);
       k_halo_pack<<<I.grid_for(hl.n_send, BLOCK * 4), BLOCK, 0, pd.stream>>>(xin[i], hl.send_idx.p, hl.n_send, hl.send_nbrs.p,
                                                                              hl.n_send_nbrs, pd.st.p, op.halo_level);
-      I.note_launch();
+      I.note_launch("k_halo_pack");
     }
   // phase 2: all rows of the own-own block (boundary rows are computed but not stored)
   for (size_t i = 0; i < I.parts.size(); ++i) {
@@ -745,7 +766,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
       const FusedHalo fh = halo_args(pd, false, true);
       LaunchArgs L{fh.n_bnd, false, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, 1, op.slot};
       launch_boundary(op.mode, op.dot, L);
-      I.note_launch();
+      I.note_launch("k_boundary");
     }
   CK(cudaGetLastError());
 }
@@ -850,6 +871,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         build_csr(pl.blk[b], false, ld.blk[b], lanes, o.spmv_format, o, b);
         build_bnd(pl.blk[b], pl.blk[b + 1], ld.bnd[b / 2]);
         max_blocks = std::max(max_blocks, ld.blk[b].nblocks);
+        max_blocks = std::max(max_blocks, (ld.blk[b].nslices + BLOCK / 32 - 1) / (BLOCK / 32));
       }
       // smoother weights
       std::vector<double> w(pl.n_own), dinv(pl.n_own);
@@ -903,7 +925,8 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         ld.asm_flags = (const uint32_t*)(pd.arena + pd.lay.asm_flags[l]);
       }
     }
-    pd.partials.alloc((size_t)max_blocks + 512);  // one partial per CTA of a fused-reduction kernel
+    pd.partials_cap = max_blocks + 8 * 148;  // one partial per CTA of a fused-reduction kernel (+ halo roles)
+    pd.partials.alloc((size_t)pd.partials_cap);
     // replicated tail: merged levels + the maps of the level it is entered through
     pd.tlev.resize(I.L);
     if (I.tail_level < I.L - 1)
@@ -945,8 +968,8 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     for (int l = 0; l < I.L; ++l) maxloc = std::max(maxloc, h->levels[l].parts[part].n_own + h->levels[l].parts[part].n_ghost);
     pd.io_local.alloc(maxloc);
   }
-  CK(cudaMallocHost(&I.pinned, sizeof(DevState) * Impl::RING));
-  for (int k = 0; k < Impl::RING; ++k) CK(cudaEventCreateWithFlags(&I.ring_ev[k], cudaEventDisableTiming));
+  CK(cudaHostAlloc(&I.hstat, sizeof(HostStat) * HS_RING, cudaHostAllocMapped | cudaHostAllocPortable));
+  std::memset(I.hstat, 0, sizeof(HostStat) * HS_RING);
   plan_buffers();
   {  // fused halo roles need every local part alone on its device (a kernel may then wait for its peers)
     std::map<int, int> per_dev;
@@ -959,6 +982,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         const PartLevel& pl = h->levels[l].parts[p];
         if (pl.recv.empty() != pl.send.empty()) symmetric = false;
       }
+    if (const char* pe = getenv("PAMG_PERSISTENT")) I.persistent = atoi(pe) != 0;
     const char* env = getenv("PAMG_FUSE_HALO");
     const bool want = env ? atoi(env) != 0 : o.fuse_halo != 0;
     I.fused_halo = want && alone && symmetric;
@@ -1270,7 +1294,7 @@ void Engine::enqueue_tail() {
     I.set_dev(pd);
     k_coarse_gather<<<I.grid_for(ld.n_own, BLOCK), BLOCK, 0, pd.stream>>>(ld.b.p, pd.own_gid_T.p, (int)ld.n_own, pd.coarse_pubs.p,
                                                                          I.nparts, pd.st.p);
-    I.note_launch();
+    I.note_launch("k_coarse_gather");
   }
   if (l == I.L - 1) {
     for (auto& up : I.parts) {
@@ -1282,7 +1306,7 @@ void Engine::enqueue_tail() {
       k_coarse_solve<<<I.grid_for(std::max(rows, 1), BLOCK / 32), BLOCK, 0, pd.stream>>>(
           pd.inv.p, n, c0, c0 + n, (const uint32_t*)(pd.arena + pd.lay.coarse_flags), I.nparts, pd.own_gid_T.p, (int)ld.n_own,
           pd.ghost_gid_T.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
-      I.note_launch();
+      I.note_launch("k_coarse_solve");
     }
     CK(cudaGetLastError());
     return;
@@ -1294,7 +1318,7 @@ void Engine::enqueue_tail() {
     const double* c0 = (const double*)(pd.arena + pd.lay.coarse);
     k_tail_in<<<I.grid_for(n, BLOCK), BLOCK, 0, pd.stream>>>(c0, c0 + n, (const uint32_t*)(pd.arena + pd.lay.coarse_flags), I.nparts,
                                                              tl.b.p, tl.xstart, o.nu_pre > 0 ? tl.w.p : nullptr, n, pd.st.p);
-    I.note_launch();
+    I.note_launch("k_tail_in");
   }
   CK(cudaGetLastError());
   I.tail_mode = true;
@@ -1312,7 +1336,7 @@ void Engine::enqueue_tail() {
     I.set_dev(pd);
     k_tail_out<<<I.grid_for(std::max<int64_t>(ld.n_own + ld.n_ghost, 1), BLOCK), BLOCK, 0, pd.stream>>>(
         tl.x.p, pd.own_gid_T.p, (int)ld.n_own, pd.ghost_gid_T.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
-    I.note_launch();
+    I.note_launch("k_tail_out");
   }
   CK(cudaGetLastError());
 }
@@ -1334,7 +1358,7 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
       I.set_dev(pd);
       k_dense<<<I.grid_for(std::max<int64_t>(ld.n_own, 1), BLOCK / 32), BLOCK, 0, pd.stream>>>(pd.inv.p, (int)ld.n_own, ld.b.p, ld.x.p,
                                                                                              pd.st.p);
-      I.note_launch();
+      I.note_launch("k_dense");
     }
     CK(cudaGetLastError());
     return;
@@ -1378,7 +1402,7 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
         LevelDev& lc = I.LV(pd, l + 1);
         I.set_dev(pd);
         k_scale<<<I.grid_for(lc.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(lc.b.p, nullptr, lc.xstart, (int)lc.n_own, pd.st.p);
-        I.note_launch();
+        I.note_launch("k_scale");
       }
   }
   enqueue_vcycle(l + 1, false);
@@ -1412,7 +1436,7 @@ void Engine::enqueue_dot_rz() {
     I.set_dev(pd);
     k_dot<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p, pd.rc,
                                                                    1, 1);
-    I.note_launch();
+    I.note_launch("k_dot");
   }
   CK(cudaGetLastError());
 }
@@ -1438,7 +1462,7 @@ void Engine::enqueue_pcg_iteration(bool precond) {
       I.set_dev(pd);
       k_copy_dot<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, (int)l0.n_own, pd.st.p, pd.partials.p,
                                                                           pd.rc);
-      I.note_launch();
+      I.note_launch("k_copy_dot");
     }
   }
   for (auto& up : I.parts) {
@@ -1446,7 +1470,7 @@ void Engine::enqueue_pcg_iteration(bool precond) {
     LevelDev& l0 = *pd.lev[0];
     I.set_dev(pd);
     k_update_p<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.x.p, pd.p.p, (int)l0.n_own, pd.st.p, pd.rc);
-    I.note_launch();
+    I.note_launch("k_update_p");
   }
   {
     std::vector<EpiArgs> epi(np);
@@ -1467,13 +1491,13 @@ void Engine::enqueue_pcg_iteration(bool precond) {
     k_update_xr<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.xsol.p, l0.b.p, pd.p.p, pd.q.p, l0.xstart,
                                                                          zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
                                                                          pd.partials.p, pd.rc);
-    I.note_launch();
+    I.note_launch("k_update_xr");
   }
   for (auto& up : I.parts) {
     PartDev& pd = *up;
     I.set_dev(pd);
-    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p);
-    I.note_launch();
+    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
+    I.note_launch("k_check");
   }
   CK(cudaGetLastError());
 }
@@ -1631,14 +1655,14 @@ double Engine::dot(int level, const double* const* u, const double* const* v) {
     LevelDev& ld = *pd.lev[level];
     I.set_dev(pd);
     k_dot<<<I.grid_red(ld.n_own), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
-    I.note_launch();
+    I.note_launch("k_dot");
   }
   double out[RED_W] = {0, 0, 0, 0};
   for (auto& up : I.parts) {
     PartDev& pd = *up;
     I.set_dev(pd);
     k_red_read<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.scratch4.p);
-    I.note_launch();
+    I.note_launch("k_red_read");
   }
   CK(cudaGetLastError());
   sync_all();
@@ -1662,7 +1686,7 @@ void Engine::consistent(int level, double* const* v) {
     I.set_dev(pd);
     k_halo_pack<<<I.grid_for(ld.n_send, BLOCK * 4), BLOCK, 0, pd.stream>>>(ld.x.p, ld.send_idx.p, ld.n_send, ld.send_nbrs.p,
                                                                            ld.n_send_nbrs, pd.st.p, level);
-    I.note_launch();
+    I.note_launch("k_halo_pack");
   }
   for (auto& up : I.parts) {
     PartDev& pd = *up;
@@ -1670,7 +1694,7 @@ void Engine::consistent(int level, double* const* v) {
     if (ld.n_recv_nbrs == 0) continue;
     I.set_dev(pd);
     k_halo_unpack<<<I.grid_for(ld.n_ghost, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.io_local.p, ld.hr, (int)ld.n_ghost, pd.st.p, level);
-    I.note_launch();
+    I.note_launch("k_halo_unpack");
     CK(cudaMemcpyAsync(v[pd.part] + ld.n_own, pd.io_local.p, ld.n_ghost * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
   }
   CK(cudaGetLastError());
@@ -1691,7 +1715,7 @@ void Engine::assemble(int level, double* const* v) {
     if (ld.n_send_nbrs == 0 && ld.n_recv_nbrs == 0) continue;
     k_asm_pack<<<I.grid_for(ld.n_ghost, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.io_local.p + ld.n_own, ld.asm_nbrs.p, ld.n_recv_nbrs,
                                                                            pd.st.p, level);
-    I.note_launch();
+    I.note_launch("k_asm_pack");
   }
   for (auto& up : I.parts) {
     PartDev& pd = *up;
@@ -1701,7 +1725,7 @@ void Engine::assemble(int level, double* const* v) {
       k_asm_add<<<I.grid_for(std::max(ld.asm_nrows, 1), BLOCK), BLOCK, 0, pd.stream>>>(
           pd.io_local.p, ld.asm_rows.p, ld.asm_ptr.p, ld.asm_src.p, ld.asm_nrows, ld.asm_stage, ld.asm_flags, ld.n_send_nbrs,
           pd.st.p, level);
-      I.note_launch();
+      I.note_launch("k_asm_add");
     }
     CK(cudaMemsetAsync(pd.io_local.p + ld.n_own, 0, ld.n_ghost * sizeof(double), pd.stream));
     CK(cudaMemcpyAsync(v[pd.part], pd.io_local.p, (ld.n_own + ld.n_ghost) * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
@@ -1722,7 +1746,7 @@ void Engine::enqueue_vcycle_entry() {
       I.set_dev(pd);
       k_scale<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.b.p, o.nu_pre > 0 ? l0.w.p : nullptr, l0.xstart,
                                                                        (int)l0.n_own, pd.st.p);
-      I.note_launch();
+      I.note_launch("k_scale");
     }
   enqueue_vcycle(0, false);
 }
@@ -1792,10 +1816,20 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
     }
   }
   if (use_graph && (I.g_iter.empty() || I.g_iter_precond != precond)) {
-    capture(I.g_iter, &I.g_iter_nodes, [&] { enqueue_pcg_iteration(precond); });
+    I.names.clear();
+    I.naming = true;
+    try {
+      capture(I.g_iter, &I.g_iter_nodes, [&] { enqueue_pcg_iteration(precond); });
+    } catch (...) {
+      I.naming = false;
+      throw;
+    }
+    I.naming = false;
     I.g_iter_precond = precond;
   }
   const bool zero_guess = precond && I.L > 1 && I.h->opts.nu_pre > 0;
+  sync_all();
+  std::memset(I.hstat, 0, sizeof(HostStat) * HS_RING);
   for (auto& up : I.parts) {
     PartDev& pd = *up;
     LevelDev& l0 = *pd.lev[0];
@@ -1804,37 +1838,45 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
     k_pcg_init<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.bsave.p, pd.xsol.p, l0.b.p, pd.p.p, l0.xstart,
                                                                         zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
                                                                         pd.partials.p, pd.rc, rtol, maxiter);
-    I.note_launch();
+    I.note_launch("k_pcg_init");
   }
   for (auto& up : I.parts) {
     PartDev& pd = *up;
     I.set_dev(pd);
-    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p);
-    I.note_launch();
+    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
+    I.note_launch("k_check");
   }
   CK(cudaGetLastError());
   // speculative enqueue: iteration k+1 is launched before the status of iteration k is known; every
   // kernel early-outs once the device-side `done` flag is set, so the extra launch is a no-op.
   PartDev& p0 = I.P(0);
   const int LOOKAHEAD = 1;
+  if (maxiter + 2 >= (1 << 30)) throw std::runtime_error("maxiter too large");
   bool finished = false;
   int launched = 0;
   while (!finished) {
     if (launched < maxiter) {
-      if (use_graph)
+      if (use_graph) {
         launch_graphs(I.g_iter, I.g_iter_nodes);
-      else
+      } else {
+        if (launched == 0) {
+          I.names.clear();
+          I.naming = true;
+        }
         enqueue_pcg_iteration(precond);
+        I.naming = false;
+      }
     }
-    I.set_dev(p0);
-    const int slot = launched % Impl::RING;
-    CK(cudaMemcpyAsync(&I.pinned[slot], p0.st.p, sizeof(DevState), cudaMemcpyDeviceToHost, p0.stream));
-    CK(cudaEventRecord(I.ring_ev[slot], p0.stream));
     ++launched;
-    if (launched > LOOKAHEAD) {
-      const int s2 = (launched - 1 - LOOKAHEAD) % Impl::RING;
-      CK(cudaEventSynchronize(I.ring_ev[s2]));
-      if (I.pinned[s2].done || I.pinned[s2].error) finished = true;
+    if (launched > LOOKAHEAD) {  // status written by k_check number (launched - LOOKAHEAD + 1), straight into pinned memory
+      const uint32_t want = (uint32_t)(launched - LOOKAHEAD + 1);
+      volatile HostStat* hsl = I.hstat + (want % HS_RING);
+      const auto t0 = std::chrono::steady_clock::now();
+      while (hsl->seq != want) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30))
+          throw CommError("timed out waiting for the device status of a PCG iteration");
+      }
+      if (hsl->done || hsl->error) finished = true;
     }
     if (launched > maxiter + LOOKAHEAD + 1) finished = true;
   }
@@ -1926,6 +1968,20 @@ void Engine::time_kernel(int kind, int level, int reps, bool flush_l2, float* ms
         I.set_dev(pd);
         k_dot<<<I.grid_red(ld.n_own), BLOCK, 0, pd.stream>>>(ld.x.p, ld.b.p, (int)ld.n_own, pd.st.p, pd.partials.p, pd.rc, 3, 0);
       }
+    } else if (kind == 8) {  // reference stream: read + write of the 256 MiB flush buffer (x += 1)
+      if (!I.flush_buf) throw std::runtime_error("kind 8 needs flush_l2 != 0");
+      k_flush<<<148 * 8, 256, 0, p0.stream>>>(I.flush_buf, I.flush_n);
+    } else if (kind == 6) {  // SpMV with the fused p.q dot (as in the PCG iteration) + its reduce launch
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& ld = *I.P(i).lev[level];
+        epi[i] = EpiArgs{ld.t.p, nullptr, nullptr, nullptr, nullptr, nullptr, ld.x.p, 0.0, 0.0};
+      }
+      enqueue_op(OpSpec{level, PAMG_A_OO, level, M_MUL, true, 3, false}, ptrs(level, V_X), epi);
+    } else if (kind == 7) {  // Jacobi sweep with the fused r.z dot
+      if (I.h->opts.smoother == PAMG_SMOOTHER_CHEBYSHEV) throw std::runtime_error("kind 7 needs a Jacobi smoother");
+      std::vector<double*> cur;
+      for (auto& up : I.parts) cur.push_back(up->lev[level]->x.p);
+      enqueue_smooth(level, 1, cur, false, true);
     } else if (kind == 5) {
       const bool use_graph = I.h->opts.use_graph != 0;
       if (use_graph && I.g_vcycle.empty()) capture(I.g_vcycle, &I.g_vcycle_nodes, [&] { enqueue_vcycle_entry(); });
@@ -1944,6 +2000,50 @@ void Engine::time_kernel(int kind, int level, int reps, bool flush_l2, float* ms
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   check_device_error();
+}
+
+// ---------------------------------------------------------------------------------------------
+// tracing: per-kernel start times (device globaltimer) of everything launched after trace_enable
+// ---------------------------------------------------------------------------------------------
+void Engine::trace_enable(int capacity) {
+  Impl& I = *impl;
+  sync_all();
+  for (auto& up : I.parts) {
+    PartDev& pd = *up;
+    I.set_dev(pd);
+    unsigned long long* buf = nullptr;
+    uint32_t zero = 0, cap = 0;
+    if (capacity > 0) {
+      pd.trace.alloc((size_t)capacity);
+      buf = pd.trace.p;
+      cap = (uint32_t)capacity;
+    }
+    CK(cudaMemcpy(&pd.st.p->trace, &buf, sizeof(buf), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&pd.st.p->trace_pos, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&pd.st.p->trace_cap, &cap, sizeof(cap), cudaMemcpyHostToDevice));
+  }
+}
+
+int Engine::trace_read(int part, unsigned long long* out, int cap) {
+  Impl& I = *impl;
+  if (part < 0 || part >= I.nparts || I.local_index[part] < 0) throw std::runtime_error("trace: part is not local");
+  PartDev& pd = I.P(I.local_index[part]);
+  sync_all();
+  I.set_dev(pd);
+  DevState s;
+  CK(cudaMemcpy(&s, pd.st.p, sizeof(s), cudaMemcpyDeviceToHost));
+  if (!s.trace) return 0;
+  const int n = (int)std::min<uint32_t>(std::min<uint32_t>(s.trace_pos, s.trace_cap), (uint32_t)std::max(cap, 0));
+  if (n > 0) CK(cudaMemcpy(out, pd.trace.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  uint32_t zero = 0;
+  CK(cudaMemcpy(&pd.st.p->trace_pos, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  return n;
+}
+
+std::string Engine::trace_names() {
+  std::string out;
+  for (auto& n : impl->names) out += n + "\n";
+  return out;
 }
 
 void Engine::get_stats(pamg_stats* s) {

@@ -53,6 +53,9 @@ class Engine {
   void read_solution(double* const* x);
   void time_kernel(int kind, int level, int reps, bool flush_l2, float* ms_out);
   void get_stats(pamg_stats* s);
+  void trace_enable(int capacity);
+  int trace_read(int part, unsigned long long* out, int cap);
+  std::string trace_names();
 
  private:
   struct Impl;

@@ -73,7 +73,17 @@ struct DevState {
   int32_t maxiter;
   double sc[SC_COUNT];
   double dot_main;  // partial of the main (own-own) kernel, completed by the own-ghost kernel
+  uint32_t check_seq;  // k_check executions since k_pcg_init
+  unsigned long long* trace;  // != nullptr: CTA 0 of every kernel appends its start time (globaltimer, ns)
+  uint32_t trace_pos, trace_cap;
 };
+
+// status record k_check stores straight into pinned host memory (no D2H copy between iterations)
+struct HostStat {
+  uint32_t seq;  // number of the k_check that wrote this slot (written last)
+  int32_t done, error, iters;
+};
+constexpr int HS_RING = 16;
 
 struct RedPub {  // where this part publishes its all-reduce contribution in part d (incl. itself)
   double* slot[2];
@@ -138,6 +148,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+// tracing: one timestamp per kernel launch, taken by the first thread of CTA 0 (pamg_trace_*)
+__device__ __forceinline__ void trace_mark(DevState* st) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && st->trace) {
+    const uint32_t i = atomicAdd(&st->trace_pos, 1u);
+    if (i < st->trace_cap) st->trace[i] = globaltimer_ns();
+  }
 }
 // streaming (read-once) 64/32-bit loads that do not pollute L1
 __device__ __forceinline__ double ldg_stream(const double* p) { return __ldcs(p); }
@@ -290,14 +307,18 @@ __device__ __forceinline__ double stream_epilogue(const EpiArgs& a, int row, dou
   return res;
 }
 
-template <int MODE>
+// loads the operands, applies the epilogue; DOT: returns dotv[row] * result with dotv read BEFORE the
+// stores (a load after the store to `out` cannot be hoisted by the compiler and would sit exposed)
+template <int MODE, bool DOT = false>
 __device__ __forceinline__ double apply_epilogue(const EpiArgs& a, int row, double s) {
-  double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0;
+  double e_in0 = 0.0, e_in1 = 0.0, e_w = 0.0, e_aux = 0.0, e_dot = 0.0;
   if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0 = a.in0[row];
   if (MODE == M_JACOBI || MODE == M_CHEB) e_in1 = a.in1[row];
   if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w = a.w[row];
   if (MODE == M_CHEB && a.aux) e_aux = a.aux[row];
-  return stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
+  if (DOT) e_dot = (a.dotv == a.in0 && (MODE == M_JACOBI || MODE == M_RESID)) ? e_in0 : a.dotv[row];
+  const double res = stream_epilogue<MODE>(a, row, s, e_in0, e_in1, e_w, e_aux);
+  return DOT ? e_dot * res : res;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,12 +333,14 @@ __device__ __forceinline__ void pack_role(const FusedHalo& fh, DevState* st, int
     while (nb + 1 < fh.n_nbrs && k >= fh.nbrs[nb + 1].offset) ++nb;
     fh.nbrs[nb].ghost[par][k - fh.nbrs[nb].offset] = fh.v[fh.send_idx[k]];
   }
-  __threadfence_system();
-  if (last_block_n(&st->ticket[1], (uint32_t)fh.n_pack)) {
-    __threadfence_system();
-    if (threadIdx.x < fh.n_nbrs) st_release_sys(fh.nbrs[threadIdx.x].flag, e);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this CTA's peer stores (cumulative over the barrier) are visible system-wide
+    const uint32_t t = atomicAdd(&st->ticket[1], 1u);
+    if (t == (uint32_t)fh.n_pack - 1u) {  // every pack CTA has fenced: publish the epoch to the neighbours
+      st->ticket[1] = 0;
+      __threadfence_system();
+      for (int nb = 0; nb < fh.n_nbrs; ++nb) *(volatile uint32_t*)fh.nbrs[nb].flag = e;
       if (fh.fused)
         *(volatile uint32_t*)&st->pack_done[fh.level] = e;  // the boundary role advances the epoch
       else
@@ -326,32 +349,61 @@ __device__ __forceinline__ void pack_role(const FusedHalo& fh, DevState* st, int
   }
 }
 
-// boundary role, CTA `bid` of fh.n_bnd: wait for the neighbours' halo, then the boundary rows whole
-// (own columns, then ghost columns, then the epilogue).  Returns this thread's dot contribution.
+// partial row sum over entries [beg, end) strided by `lanes`, four entries in flight per lane
+template <bool VOLATILE_X>
+__device__ __forceinline__ double row_part(const int32_t* __restrict__ col, const double* __restrict__ val, int beg, int end,
+                                           int lane, int lanes, const double* x) {
+  double s = 0.0;
+  for (int q = beg + lane; q < end; q += 4 * lanes) {
+    int c[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int qq = q + u * lanes;
+      c[u] = qq < end ? ldg_stream(col + qq) : -1;
+      v[u] = qq < end ? ldg_stream(val + qq) : 0.0;
+    }
+    double xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = c[u] >= 0 ? (VOLATILE_X ? __ldcv(x + c[u]) : x[c[u]]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += v[u] * xv[u];
+  }
+  return s;
+}
+
+// boundary role, CTA `bid` of fh.n_bnd: the boundary rows whole -- own-column sum first (it does not
+// need the halo, so it runs while the neighbours' values are still in flight), then wait for the
+// neighbours' flags, ghost-column sum, epilogue.  Returns this thread's dot contribution.
 template <int MODE, bool DOT>
 __device__ __forceinline__ double boundary_role(const FusedHalo& fh, const double* __restrict__ x, const EpiArgs& a, DevState* st,
                                                 int bid) {
   __shared__ int s_par;
   __shared__ uint32_t s_epoch;
-  if (threadIdx.x == 0) {
-    if (fh.fixed_parity >= 0) {
-      s_par = fh.fixed_parity;
-      s_epoch = 0;
-    } else {
-      const uint32_t e = *(volatile uint32_t*)&st->halo_epoch[fh.level] + (fh.fused ? 1u : 0u);
-      s_par = halo_wait(fh.hr, e, st);
-      s_epoch = e;
-    }
-  }
-  __syncthreads();
-  const double* g = fh.hr.ghost[s_par];
   const BndView& B = fh.B;
   const int lanes = B.lanes;
   const int lane = threadIdx.x & (lanes - 1);
   const int grp = threadIdx.x / lanes;
   const int rpb = BLOCK / lanes;
+  bool waited = false;
+  const double* g = nullptr;
+  auto wait_halo = [&]() {  // block-uniform call sites only
+    if (threadIdx.x == 0) {
+      if (fh.fixed_parity >= 0) {
+        s_par = fh.fixed_parity;
+        s_epoch = 0;
+      } else {
+        const uint32_t e = *(volatile uint32_t*)&st->halo_epoch[fh.level] + (fh.fused ? 1u : 0u);
+        s_par = halo_wait(fh.hr, e, st);
+        s_epoch = e;
+      }
+    }
+    __syncthreads();
+    g = fh.hr.ghost[s_par];
+    waited = true;
+  };
   double acc = 0.0;
-  // block-uniform trip count: every lane reaches the full-mask shuffles
+  // block-uniform trip count: every lane reaches the barrier and the full-mask shuffles
   for (int k0 = bid * rpb; k0 < B.n; k0 += fh.n_bnd * rpb) {
     const int k = k0 + grp;
     const bool valid = k < B.n;
@@ -361,26 +413,20 @@ __device__ __forceinline__ double boundary_role(const FusedHalo& fh, const doubl
       mid = B.mid[k];
       end = B.ptr[k + 1];
     }
-    double s = 0.0, sg = 0.0;
-    if (lanes == 1) {  // short rows: one thread per row, unit stride so that the loads are batched
-#pragma unroll 4
-      for (int q = beg; q < mid; ++q) s += ldg_stream(B.val + q) * x[ldg_stream(B.col + q)];
-#pragma unroll 4
-      for (int q = mid; q < end; ++q) sg += ldg_stream(B.val + q) * __ldcv(g + ldg_stream(B.col + q));
-    } else {
-      for (int q = beg + lane; q < mid; q += lanes) s += ldg_stream(B.val + q) * x[ldg_stream(B.col + q)];
-      for (int q = mid + lane; q < end; q += lanes) sg += ldg_stream(B.val + q) * __ldcv(g + ldg_stream(B.col + q));
-      for (int o = lanes >> 1; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      }
+    double s = row_part<false>(B.col, B.val, beg, mid, lane, lanes, x);
+    if (!waited) wait_halo();
+    double sg = row_part<true>(B.col, B.val, mid, end, lane, lanes, g);
+    for (int o = lanes >> 1; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
     }
     if (valid && lane == 0) {
       const int row = B.rows[k];
-      const double res = apply_epilogue<MODE>(a, row, s + sg);  // mul!: own-own sum, then += own-ghost sum
-      if (DOT) acc += a.dotv[row] * res;
+      const double res = apply_epilogue<MODE, DOT>(a, row, s + sg);  // mul!: own-own sum, then += own-ghost sum
+      if (DOT) acc += res;
     }
   }
+  if (!waited) wait_halo();  // a CTA without rows still consumes the exchange (keeps the epoch protocol in step)
   if (fh.fused && fh.fixed_parity < 0 && last_block_n(&st->ticket[4], (uint32_t)fh.n_bnd)) {
     if (threadIdx.x == 0) {  // every boundary CTA has consumed epoch e: advance once the local pack is out
       const uint32_t e = s_epoch;
@@ -398,6 +444,7 @@ template <int LANES, int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
                                                  double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
+  trace_mark(st);
   double acc = 0.0;
   int bid = blockIdx.x;
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
@@ -430,8 +477,8 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
       }
       s = group_sum<LANES>(s);
       if (valid && lane == 0 && !sk) {
-        const double res = apply_epilogue<MODE>(a, r, s);
-        if (DOT) acc += a.dotv[r] * res;
+        const double res = apply_epilogue<MODE, DOT>(a, r, s);
+        if (DOT) acc += res;
       }
     }
   }
@@ -443,6 +490,7 @@ template <int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK) k_boundary(const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
                                                      double* partials, RedCtx rc, int red_slot) {
   if (st->done) return;
+  trace_mark(st);
   const double acc = boundary_role<MODE, DOT>(fh, x, a, st, blockIdx.x);
   if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, 1, 1, red_slot);
 }
@@ -483,11 +531,13 @@ template <int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const double* __restrict__ x, EpiArgs a, DevState* st,
                                                         FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
+  trace_mark(st);
   __shared__ double prod[S_STEPS * 4 * BLOCK];
   const int t = threadIdx.x;
   double acc = 0.0;
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
   int bk0 = (int)blockIdx.x - fh.n_pack - fh.n_bnd;
+#ifndef PAMG_NO_ROLES
   if ((int)blockIdx.x < fh.n_pack) {
     pack_role(fh, st, blockIdx.x);
     bk0 = A.nblocks;  // no main work
@@ -495,6 +545,7 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
     acc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - fh.n_pack);
     bk0 = A.nblocks;
   }
+#endif
   for (int bk = bk0; bk < A.nblocks; bk += n_main) {
     const int2 b0 = A.blk[bk], b1 = A.blk[bk + 1];
     const int r0 = b0.x, nr = b1.x - b0.x;
@@ -615,8 +666,10 @@ template <int RPT, int MODE, bool DOT>
 __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView A, const double* __restrict__ x, EpiArgs a, DevState* st,
                                                       FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
+  trace_mark(st);
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
   const int bid = (int)blockIdx.x - fh.n_pack - fh.n_bnd;
+#ifndef PAMG_NO_ROLES
   if (bid < 0) {  // halo roles
     double racc = 0.0;
     if ((int)blockIdx.x < fh.n_pack)
@@ -626,6 +679,7 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
     if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
     return;
   }
+#endif
   using V = typename SellVec<RPT>::V;
   using I = typename SellVec<RPT>::I;
   constexpr int U = RPT == 1 ? 8 : 4;  // entries of a row in flight per step
@@ -635,35 +689,34 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
   for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
     const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
     const int slot0 = sl * (32 * RPT) + lane * RPT;
-    int row[RPT];
-    double s[RPT];
-    unsigned char sk[RPT];  // requested before the entries are streamed, tested only in the epilogue
+    // Nothing but the row sums stays in registers across the entry loop: the epilogue operands, the skip
+    // flags and (with a permutation) the row ids are prefetched into L1 here and loaded after the loop.
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       const int slot = slot0 + k;
-      row[k] = -1;
-      s[k] = 0.0;
-      sk[k] = 0;
       if (slot < A.nrows) {
         const int r = A.perm ? A.perm[slot] : slot;
-        row[k] = r;
-        if (fh.skip) sk[k] = fh.skip[r];
+        if (fh.skip) asm volatile("prefetch.global.L1 [%0];" ::"l"(fh.skip + r));
         if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) prefetch_l1(a.in0 + r);
         if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) prefetch_l1(a.w + r);
         if (MODE == M_CHEB && a.aux) prefetch_l1(a.aux + r);
         if (DOT && a.dotv != a.in0) prefetch_l1(a.dotv + r);
       }
     }
-    const V* __restrict__ vp = reinterpret_cast<const V*>(A.val) + (size_t)o0 * 32 + lane;
-    const I* __restrict__ cp = reinterpret_cast<const I*>(A.col) + (size_t)o0 * 32 + lane;
-    for (int j0 = 0; j0 < w; j0 += U) {
+    double s[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) s[k] = 0.0;
+    const V* __restrict__ vj = reinterpret_cast<const V*>(A.val) + (size_t)o0 * 32 + lane;
+    const I* __restrict__ cj = reinterpret_cast<const I*>(A.col) + (size_t)o0 * 32 + lane;
+#pragma unroll 1
+    for (int j0 = 0; j0 < w; j0 += U, vj += U * 32, cj += U * 32) {
       V v[U];
       I c[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (j0 + u < w) {
-          c[u] = __ldcs(cp + (size_t)(j0 + u) * 32);
-          v[u] = __ldcs(vp + (size_t)(j0 + u) * 32);
+          c[u] = __ldcs(cj + u * 32);
+          v[u] = __ldcs(vj + u * 32);
         }
       double xv[U][RPT];
 #pragma unroll
@@ -679,12 +732,18 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
           for (int k = 0; k < RPT; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(sv_get(v[u], k), xv[u][k]));
         }
     }
+    double contrib = 0.0;
 #pragma unroll
-    for (int k = 0; k < RPT; ++k)
-      if (row[k] >= 0 && !sk[k]) {
-        const double res = apply_epilogue<MODE>(a, row[k], s[k]);
-        if (DOT) acc += a.dotv[row[k]] * res;
+    for (int k = 0; k < RPT; ++k) {
+      const int slot = slot0 + k;
+      if (slot < A.nrows) {
+        const int r = A.perm ? A.perm[slot] : slot;
+        if (fh.skip && fh.skip[r]) continue;
+        const double res = apply_epilogue<MODE, DOT>(a, r, s[k]);
+        if (DOT) contrib += res;
       }
+    }
+    if (DOT) acc += contrib;
   }
   if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }
@@ -696,6 +755,7 @@ __global__ void __launch_bounds__(BLOCK) k_halo_pack(const double* __restrict__ 
                                                       int n_send, const SendNbr* __restrict__ nbrs, int n_nbrs,
                                                       DevState* st, int level) {
   if (st->done) return;
+  trace_mark(st);
   const uint32_t e = *(volatile uint32_t*)&st->halo_epoch[level] + 1u;
   const int par = (int)(e & 1u);
   for (int k = blockIdx.x * BLOCK + threadIdx.x; k < n_send; k += gridDim.x * BLOCK) {
@@ -769,6 +829,7 @@ __global__ void __launch_bounds__(BLOCK) k_coarse_gather(const double* __restric
                                                           int n_own, const CoarsePub* __restrict__ pubs, int nparts,
                                                           DevState* st) {
   if (st->done) return;
+  trace_mark(st);
   const uint32_t e = *(volatile uint32_t*)&st->coarse_epoch + 1u;
   const int par = (int)(e & 1u);
   for (int d = 0; d < nparts; ++d)
@@ -788,6 +849,7 @@ __global__ void __launch_bounds__(BLOCK) k_coarse_solve(const double* __restrict
                                                          const int64_t* __restrict__ ghost_gid, int n_ghost,
                                                          double* __restrict__ x, double* __restrict__ xg, DevState* st) {
   if (st->done) return;
+  trace_mark(st);
   __shared__ int s_par;
   if (threadIdx.x == 0) {
     const uint32_t e = *(volatile uint32_t*)&st->coarse_epoch;
@@ -827,6 +889,7 @@ __global__ void __launch_bounds__(BLOCK) k_tail_in(const double* g0, const doubl
                                                     double* __restrict__ b, double* __restrict__ xstart,
                                                     const double* __restrict__ w, int n, DevState* st) {
   if (st->done) return;
+  trace_mark(st);
   __shared__ int s_par;
   if (threadIdx.x == 0) {
     const uint32_t e = *(volatile uint32_t*)&st->coarse_epoch;
@@ -846,6 +909,7 @@ __global__ void __launch_bounds__(BLOCK) k_tail_in(const double* g0, const doubl
 __global__ void __launch_bounds__(BLOCK) k_dense(const double* __restrict__ inv, int n, const double* __restrict__ b,
                                                   double* __restrict__ x, DevState* st) {
   if (st->done) return;
+  trace_mark(st);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * BLOCK) >> 5;
@@ -862,6 +926,7 @@ __global__ void __launch_bounds__(BLOCK) k_tail_out(const double* __restrict__ x
                                                      const int64_t* __restrict__ ghost_gid, int n_ghost, double* __restrict__ x,
                                                      double* __restrict__ xg, DevState* st) {
   if (st->done) return;
+  trace_mark(st);
   for (int r = blockIdx.x * BLOCK + threadIdx.x; r < n_own + n_ghost; r += gridDim.x * BLOCK) {
     if (r < n_own)
       x[r] = xfull[own_gid[r]];
@@ -877,6 +942,7 @@ __global__ void __launch_bounds__(BLOCK) k_tail_out(const double* __restrict__ x
 __global__ void __launch_bounds__(BLOCK) k_pcg_init(const double* __restrict__ b, double* __restrict__ x, double* __restrict__ r,
                                                      double* __restrict__ p, double* __restrict__ z0, const double* __restrict__ w,
                                                      int n, DevState* st, double* partials, RedCtx rc, double rtol, int maxiter) {
+  trace_mark(st);
   double acc = 0.0;
   for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
     const double bi = b[i];
@@ -888,6 +954,7 @@ __global__ void __launch_bounds__(BLOCK) k_pcg_init(const double* __restrict__ b
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->done = 0;
+    st->check_seq = 0;
     st->iters = -1;  // the first k_check (of r0) brings it to 0
     st->maxiter = maxiter;
     st->sc[SC_RHO_OLD] = __longlong_as_double(0x7ff0000000000000ll);  // +inf => first beta = 0
@@ -897,24 +964,37 @@ __global__ void __launch_bounds__(BLOCK) k_pcg_init(const double* __restrict__ b
 }
 
 // consume ||r||^2; record history; decide convergence (identically on every part)
-__global__ void k_check(DevState* st, RedCtx rc, double* hist) {
-  if (st->done) return;
-  double v[RED_W];
-  red_consume(st, rc, v);
-  const double rr = v[0];
-  const int it = st->iters + 1;
-  st->iters = it;
-  if (it == 0) st->sc[SC_RR0] = rr;
-  st->sc[SC_RR] = rr;
-  if (hist) hist[it] = sqrt(rr);
-  const double rtol = st->sc[SC_RTOL];  // same test as the oracle: ||r|| <= rtol ||r0||
-  if (sqrt(rr) <= rtol * sqrt(st->sc[SC_RR0]) || it >= st->maxiter) st->done = 1;
+__global__ void k_check(DevState* st, RedCtx rc, double* hist, HostStat* hs) {
+  if (!st->done) {
+    trace_mark(st);
+    double v[RED_W];
+    red_consume(st, rc, v);
+    const double rr = v[0];
+    const int it = st->iters + 1;
+    st->iters = it;
+    if (it == 0) st->sc[SC_RR0] = rr;
+    st->sc[SC_RR] = rr;
+    if (hist) hist[it] = sqrt(rr);
+    const double rtol = st->sc[SC_RTOL];  // same test as the oracle: ||r|| <= rtol ||r0||
+    if (sqrt(rr) <= rtol * sqrt(st->sc[SC_RR0]) || it >= st->maxiter) st->done = 1;
+  }
+  if (hs) {  // the host polls this ring instead of copying DevState between the iterations' graphs
+    const uint32_t seq = st->check_seq + 1u;
+    st->check_seq = seq;
+    HostStat* h = hs + (seq % HS_RING);
+    h->done = st->done;
+    h->error = st->error;
+    h->iters = st->iters;
+    __threadfence_system();
+    *(volatile uint32_t*)&h->seq = seq;
+  }
 }
 
 // beta = rz / rho_old ; p = z + beta p
 __global__ void __launch_bounds__(BLOCK) k_update_p(const double* __restrict__ z, double* __restrict__ p, int n, DevState* st,
                                                      RedCtx rc) {
   if (st->done) return;
+  trace_mark(st);
   __shared__ double s_beta;
   if (threadIdx.x == 0) {
     double v[RED_W];
@@ -933,6 +1013,7 @@ __global__ void __launch_bounds__(BLOCK) k_update_xr(double* __restrict__ x, dou
                                                       const double* __restrict__ w, int n, DevState* st, double* partials,
                                                       RedCtx rc) {
   if (st->done) return;
+  trace_mark(st);
   __shared__ double s_alpha;
   if (threadIdx.x == 0) {
     double v[RED_W];
@@ -968,6 +1049,7 @@ __global__ void __launch_bounds__(BLOCK) k_update_xr(double* __restrict__ x, dou
 __global__ void __launch_bounds__(BLOCK) k_copy_dot(const double* __restrict__ r, double* __restrict__ z, int n, DevState* st,
                                                      double* partials, RedCtx rc) {
   if (st->done) return;
+  trace_mark(st);
   double acc = 0.0;
   for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
     const double ri = r[i];
@@ -981,6 +1063,7 @@ __global__ void __launch_bounds__(BLOCK) k_copy_dot(const double* __restrict__ r
 __global__ void __launch_bounds__(BLOCK) k_scale(const double* __restrict__ b, const double* __restrict__ w, double* __restrict__ out,
                                                   int n, DevState* st) {
   if (st->done) return;
+  trace_mark(st);
   for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) out[i] = w ? w[i] * b[i] : 0.0;
 }
 
@@ -988,6 +1071,7 @@ __global__ void __launch_bounds__(BLOCK) k_scale(const double* __restrict__ b, c
 __global__ void __launch_bounds__(BLOCK) k_dot(const double* __restrict__ u, const double* __restrict__ v, int n, DevState* st,
                                                 double* partials, RedCtx rc, int slot, int honor_done) {
   if (honor_done && st->done) return;
+  trace_mark(st);
   double acc = 0.0;
   for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) acc += u[i] * v[i];
   dot_finish(acc, partials, st, &st->ticket[0], rc, 1, 0, slot);

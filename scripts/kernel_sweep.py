@@ -57,9 +57,16 @@ for name, kw in CONFIGS.items():
         p_b = 12 * info.nnz[2] + 4 * (nr + 1) + 8 * nc + 16 * nr
         r_b = 12 * info.nnz[4] + 4 * (nc + 1) + 8 * nr + 8 * nc
         algo = {0: ("spmv", a_b), 1: ("jacobi", a_b + 16 * nr), 2: ("resid+restrict", a_b + 8 * nr + r_b), 3: ("prolong", p_b)}
+        if lvl == 0:
+            algo.update({6: ("spmv+dot", a_b), 7: ("jacobi+dot", a_b + 16 * nr)})
         for kind, (kn, nb) in algo.items():
             ms = float(np.mean(c.time_kernel(kind, lvl, 9, True)[2:]))
             row[f"L{lvl}.{kn}"] = dict(ms=round(ms, 4), gbs=round(nb / ms / 1e6, 1), frac=round(nb / ms / 1e6 / PEAK, 3))
+    try:
+        ref_ms = float(np.mean(c.time_kernel(8, 0, 9, True)[2:]))
+        row["stream_ref"] = dict(ms=round(ref_ms, 4), gbs=round(2 * (256 << 20) / ref_ms / 1e6, 1))
+    except Exception:
+        pass
     row["fill"] = [round(st.sell_fill[l], 3) for l in range(c.num_levels())]
     res[name] = row
     print(name, json.dumps(row), flush=True)
