@@ -124,6 +124,7 @@ struct FusedHalo {
   int32_t level;            // halo level (epoch / flag index)
   int32_t fixed_parity;     // >= 0: ghost values are already in staging[parity], no wait (coarsest level)
   int32_t fused;            // 1: roles inside one launch (boundary role advances the epoch)
+  int32_t bnd_first;        // 1: block ids [pack | boundary | main]; 0: [pack | main | boundary]
   int32_t n_send, n_nbrs;   // pack role
   const double* v;
   const int32_t* send_idx;
@@ -448,12 +449,13 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(CsrView A, const double* __restr
   double acc = 0.0;
   int bid = blockIdx.x;
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
+  const int b0 = fh.n_pack + (fh.bnd_first ? 0 : n_main);  // first boundary CTA
   if (bid < fh.n_pack) {
     pack_role(fh, st, bid);
-  } else if (bid < fh.n_pack + fh.n_bnd) {
-    acc = boundary_role<MODE, DOT>(fh, x, a, st, bid - fh.n_pack);
+  } else if (bid >= b0 && bid < b0 + fh.n_bnd) {
+    acc = boundary_role<MODE, DOT>(fh, x, a, st, bid - b0);
   } else {
-    bid -= fh.n_pack + fh.n_bnd;
+    bid -= fh.n_pack + (fh.bnd_first ? fh.n_bnd : 0);
     constexpr int RPB = BLOCK / LANES;
     const int lane = threadIdx.x % LANES;
     const int grp = threadIdx.x / LANES;
@@ -536,16 +538,15 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
   const int t = threadIdx.x;
   double acc = 0.0;
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
-  int bk0 = (int)blockIdx.x - fh.n_pack - fh.n_bnd;
-#ifndef PAMG_NO_ROLES
+  int bk0 = (int)blockIdx.x - fh.n_pack - (fh.bnd_first ? fh.n_bnd : 0);
+  const int b0 = fh.n_pack + (fh.bnd_first ? 0 : n_main);  // first boundary CTA
   if ((int)blockIdx.x < fh.n_pack) {
     pack_role(fh, st, blockIdx.x);
     bk0 = A.nblocks;  // no main work
-  } else if (bk0 < 0) {
-    acc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - fh.n_pack);
+  } else if ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + fh.n_bnd) {
+    acc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - b0);
     bk0 = A.nblocks;
   }
-#endif
   for (int bk = bk0; bk < A.nblocks; bk += n_main) {
     const int2 b0 = A.blk[bk], b1 = A.blk[bk + 1];
     const int r0 = b0.x, nr = b1.x - b0.x;
@@ -668,18 +669,17 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
   if (st->done) return;
   trace_mark(st);
   const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
-  const int bid = (int)blockIdx.x - fh.n_pack - fh.n_bnd;
-#ifndef PAMG_NO_ROLES
-  if (bid < 0) {  // halo roles
+  const int bid = (int)blockIdx.x - fh.n_pack - (fh.bnd_first ? fh.n_bnd : 0);
+  const int b0 = fh.n_pack + (fh.bnd_first ? 0 : n_main);  // first boundary CTA
+  if ((int)blockIdx.x < fh.n_pack || ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + fh.n_bnd)) {  // halo roles
     double racc = 0.0;
     if ((int)blockIdx.x < fh.n_pack)
       pack_role(fh, st, blockIdx.x);
     else
-      racc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - fh.n_pack);
+      racc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - b0);
     if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
     return;
   }
-#endif
   using V = typename SellVec<RPT>::V;
   using I = typename SellVec<RPT>::I;
   constexpr int U = RPT == 1 ? 8 : 4;  // entries of a row in flight per step
