@@ -30,7 +30,19 @@ WORKLOADS = {
     "poisson3d-256": dict(dims=(256, 256, 256), desc="3D Poisson 7-point 256^3 (16.7M DOF), b=A*xstar, x0=0, rtol 1e-8"),
     "poisson3d-128": dict(dims=(128, 128, 128), desc="3D Poisson 7-point 128^3 (2.1M DOF), b=A*xstar, x0=0, rtol 1e-8"),
     "poisson3d-64": dict(dims=(64, 64, 64), desc="3D Poisson 7-point 64^3 (262k DOF), b=A*xstar, x0=0, rtol 1e-8"),
+    # BASELINE.json configs[3]: 27-point node stencil, 3 DOFs per node, rigid-body near-nullspace SA
+    "elasticity3d-96": dict(dims=(96, 96, 96), kind="elasticity",
+                            desc="3D linear elasticity Q1, 96^3 nodes x 3 DOF (2.65M DOF), rigid-body SA, b=A*xstar, x0=0, rtol 1e-8"),
+    "elasticity3d-48": dict(dims=(48, 48, 48), kind="elasticity",
+                            desc="3D linear elasticity Q1, 48^3 nodes x 3 DOF (332k DOF), rigid-body SA, b=A*xstar, x0=0, rtol 1e-8"),
 }
+
+
+def make_problem(c, wl, nparts):
+    if wl.get("kind") == "elasticity":
+        c.gallery_elasticity(wl["dims"], PARTS[nparts])
+    else:
+        c.gallery_poisson(wl["dims"], PARTS[nparts])
 PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 RTOL, MAXITER = 1e-8, 200
 
@@ -173,7 +185,7 @@ def run_reference(args, wl, rank, world):
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)  # the C oracle uses every host core
     c = L.Context(nparts)
     dims = wl["dims"]
-    c.gallery_poisson(dims, PARTS[nparts])
+    make_problem(c, wl, nparts)
     c.setup()
     n, nnz = c.global_size()
     b = c.host_matvec_global(xstar(n))
@@ -241,7 +253,7 @@ def main():
     L.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))  # torchrun exports OMP_NUM_THREADS=1
     c = L.Context(nparts)
     t0 = time.perf_counter()
-    c.gallery_poisson(dims, PARTS[nparts])
+    make_problem(c, wl, nparts)
     # host setup is replicated on every rank (deterministic); run it in waves so that the box's memory
     # holds the concurrent copies (256^3 needs ~13 GB per process while building)
     if world > 1:
@@ -249,7 +261,7 @@ def main():
             avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
         except Exception:
             avail = 64 << 30
-        need = 1000 * int(np.prod(dims))  # bytes, generous
+        need = 1000 * int(np.prod(dims)) * (30 if wl.get("kind") == "elasticity" else 1)  # bytes, generous
         per_wave = max(1, min(world, int(0.6 * avail // need)))
         for w0 in range(0, world, per_wave):
             if w0 <= rank < w0 + per_wave:

@@ -127,6 +127,18 @@ int pamg_gallery_poisson(pamg_ctx* c, int32_t ndim, const int64_t* nodes_per_dir
 int pamg_gallery_diffusion_jump(pamg_ctx* c, int32_t ndim, const int64_t* nodes_per_dir,
                                 const int32_t* parts_per_dir, int32_t blocks, double kmax,
                                 double eps_z);
+/* 3-D linear elasticity (BASELINE.json configs[3]): trilinear hexahedra on unit cubes, nodes_per_dir FREE nodes
+ * with 3 DOFs each (gid = 3 node + component), the node layer at i = -1 clamped and eliminated; also installs
+ * the 6 rigid-body modes as near-nullspace (PartitionedArrays `linear_elasticity_fem` +
+ * `nullspace_linear_elasticity`).  Nodes, not DOFs, are partitioned. */
+int pamg_gallery_elasticity(pamg_ctx* c, const int64_t* nodes_per_dir, const int32_t* parts_per_dir, double E,
+                            double nu);
+/* near-nullspace B (row-major n x k, GLOBAL row order) and the number of DOFs per node: the setup then
+ * aggregates nodes and builds the tentative prolongator by per-aggregate QR of B (PartitionedSolvers
+ * `smoothed_aggregation(; tentative_prolongator = ... with_block_size / near nullspace)`); k <= 0 or B == NULL
+ * restores scalar smoothed aggregation.  Call after the matrix is set, before pamg_setup. */
+int pamg_set_near_nullspace(pamg_ctx* c, int32_t block_size, int32_t k, const double* B);
+int pamg_get_near_nullspace(pamg_ctx* c, int32_t* block_size, int32_t* k, double* B /* may be NULL */);
 int pamg_uniform_partition(int32_t ndim, const int64_t* nodes_per_dir,
                            const int32_t* parts_per_dir, int32_t* owner_out);
 /* y = A x on the global host matrix (builds right-hand sides b = A*1 without a second copy) */

@@ -53,6 +53,8 @@ DEFAULTS = dict(
     cheb_degree=3,
     cheb_lo_frac=1.0 / 30.0,
     cheb_hi_frac=1.0,
+    block_size=1,         # DOFs per node on level 0 (3 for elasticity); aggregation works on nodes
+    nullspace=None,       # near-nullspace B (n x k, e.g. the 6 rigid-body modes): tentative P by per-aggregate QR
 )
 
 
@@ -150,6 +152,172 @@ def jump_coefficient_k(nodes_per_dir, blocks=8, kmax=1.0e4, eps_z=1.0e-3):
         return tuple(out)
 
     return kfun
+
+
+
+# ---- 3-D linear elasticity, trilinear (Q1) hexahedra on unit cubes (BASELINE.json configs[3]) ----
+def _elasticity_tables():
+    """Integer element tables: Ke[(a,d),(b,e)] = (lam * NL + mu * NM) / 72 for the unit cube, local node
+    a = ax + 2 ay + 4 az.  G72[a,b,d,e] = 72 * int d_d(phi_a) d_e(phi_b): +-{8,4,2} for d == e, +-{6,3} else."""
+    G = np.zeros((8, 8, 3, 3), dtype=np.int64)
+    for a in range(8):
+        for b in range(8):
+            ab = [(a >> m) & 1 for m in range(3)]
+            bb = [(b >> m) & 1 for m in range(3)]
+            for d in range(3):
+                for e in range(3):
+                    if d == e:
+                        v = (2 * ab[d] - 1) * (2 * bb[d] - 1) * 2
+                        for m in range(3):
+                            if m != d:
+                                v *= 2 if ab[m] == bb[m] else 1
+                    else:
+                        m = 3 - d - e
+                        v = (2 * ab[d] - 1) * (2 * bb[e] - 1) * (6 if ab[m] == bb[m] else 3)
+                    G[a, b, d, e] = v
+    NL = np.zeros((8, 8, 3, 3), dtype=np.int64)
+    NM = np.zeros((8, 8, 3, 3), dtype=np.int64)
+    for d in range(3):
+        for e in range(3):
+            NL[:, :, d, e] = G[:, :, d, e]
+            NM[:, :, d, e] = G[:, :, e, d]
+            if d == e:
+                NM[:, :, d, e] += G[:, :, 0, 0] + G[:, :, 1, 1] + G[:, :, 2, 2]
+    return NL, NM
+
+
+def elasticity_q1(nodes_per_dir, E=1.0, nu=0.25):
+    """Stiffness matrix of isotropic linear elasticity on an nx x ny x nz grid of FREE nodes (3 DOFs each,
+    gid = 3 * node + component, node = i + nx (j + ny k)); the layer of nodes at i = -1 is clamped and
+    eliminated, so the elements with lower corner cx = -1 only feed the diagonal side.  Every (node,
+    neighbour-node) 3x3 block is stored whole (explicit zeros included).  Entries are
+    (lam * sum NL + mu * sum NM) / 72 with the element sums done in integers [DEFINED-HERE], so the C++
+    gallery reproduces them bit for bit.  Returns (A, coords) with coords[node] = (i + 1, j, k)."""
+    nx, ny, nz = (int(d) for d in nodes_per_dir)
+    lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    mu = E / (2.0 * (1.0 + nu))
+    NL, NM = _elasticity_tables()
+    rows, cols, vl, vm = [], [], [], []
+    cx, cy, cz = np.meshgrid(np.arange(-1, nx - 1), np.arange(0, max(ny - 1, 0)), np.arange(0, max(nz - 1, 0)), indexing="ij")
+    cx, cy, cz = cx.ravel(), cy.ravel(), cz.ravel()
+    for a in range(8):
+        ia, ja, ka = cx + (a & 1), cy + ((a >> 1) & 1), cz + ((a >> 2) & 1)
+        for b in range(8):
+            ib, jb, kb = cx + (b & 1), cy + ((b >> 1) & 1), cz + ((b >> 2) & 1)
+            ok = (ia >= 0) & (ib >= 0)
+            na = (ia + nx * (ja + ny * ka))[ok]
+            nb = (ib + nx * (jb + ny * kb))[ok]
+            for d in range(3):
+                for e in range(3):
+                    rows.append(3 * na + d)
+                    cols.append(3 * nb + e)
+                    vl.append(np.full(len(na), NL[a, b, d, e], dtype=np.int64))
+                    vm.append(np.full(len(na), NM[a, b, d, e], dtype=np.int64))
+    n = 3 * nx * ny * nz
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    SL = sp.coo_matrix((np.concatenate(vl), (rows, cols)), shape=(n, n)).tocsr()
+    SM = sp.coo_matrix((np.concatenate(vm), (rows, cols)), shape=(n, n)).tocsr()
+    SL.sort_indices()
+    SM.sort_indices()
+    assert np.array_equal(SL.indptr, SM.indptr) and np.array_equal(SL.indices, SM.indices)
+    data = (lam * SL.data.astype(np.float64) + mu * SM.data.astype(np.float64)) / 72.0
+    A = sp.csr_matrix((data, SL.indices, SL.indptr), shape=(n, n))
+    node = np.arange(nx * ny * nz, dtype=np.int64)
+    coords = np.stack([(node % nx) + 1.0, ((node // nx) % ny).astype(np.float64), (node // (nx * ny)).astype(np.float64)], axis=1)
+    return _as64(A), coords
+
+
+def rigid_body_modes(coords):
+    """Near-nullspace of 3-D elasticity: 3 translations + 3 rotations (u = w x r) about the coordinate axes
+    through the origin, (3 n_nodes) x 6."""
+    n = len(coords)
+    x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+    B = np.zeros((3 * n, 6))
+    B[0::3, 0] = 1.0
+    B[1::3, 1] = 1.0
+    B[2::3, 2] = 1.0
+    B[1::3, 3], B[2::3, 3] = -z, y
+    B[0::3, 4], B[2::3, 4] = z, -x
+    B[0::3, 5], B[1::3, 5] = -y, x
+    return B
+
+
+def householder_qr(Bm):
+    """Thin QR of an m x k block by Householder reflections [DEFINED-HERE, mirrored by host_setup.cpp]:
+    diag(R) >= 0; a sub-column whose norm is <= 1e-12 of the original column's norm is treated as exactly
+    zero (no reflector, R_jj = 0), which makes rank-deficient aggregates (collinear nodes) reproducible;
+    m < k pads Q with zero columns and R with zero rows.  Returns Q (m x k), R (k x k)."""
+    m, k = Bm.shape
+    r = min(m, k)
+    W = np.array(Bm, dtype=np.float64, copy=True)
+    cn = np.sqrt((W * W).sum(axis=0))
+    refl = []
+    for j in range(r):
+        xcol = W[j:, j].copy()
+        alpha = float(np.sqrt((xcol * xcol).sum()))
+        if alpha <= 1e-12 * cn[j] or cn[j] == 0.0:
+            W[j:, j] = 0.0
+            refl.append(None)
+            continue
+        beta = -alpha if xcol[0] >= 0.0 else alpha
+        v = xcol
+        v[0] -= beta
+        vn2 = float((v * v).sum())
+        W[j:, j:] -= np.outer(v, (2.0 / vn2) * (v @ W[j:, j:]))
+        W[j + 1:, j] = 0.0
+        refl.append((v, vn2))
+    R = np.zeros((k, k))
+    R[:r, :] = np.triu(W[:r, :])
+    Q = np.zeros((m, k))
+    Q[:r, :r] = np.eye(r)
+    for j in range(r - 1, -1, -1):
+        if refl[j] is None:
+            continue
+        v, vn2 = refl[j]
+        Q[j:, :r] -= np.outer(v, (2.0 / vn2) * (v @ Q[j:, :r]))
+    for j in range(r):
+        if R[j, j] < 0.0:
+            R[j, :] = -R[j, :]
+            Q[:, j] = -Q[:, j]
+    return Q, R
+
+
+def tentative_from_nullspace(B, agg_node, n_agg, bs):
+    """P0 (n x k*n_agg, every row of an aggregate stores all k entries) and the coarse near-nullspace
+    (k*n_agg x k) from per-aggregate QR of B; `dead` lists coarse DOFs whose P0 column is identically
+    zero (aggregates with fewer rows than k): their Galerkin diagonal is set to 1."""
+    n, k = B.shape
+    order = np.argsort(agg_node, kind="stable")
+    bounds = np.searchsorted(agg_node[order], np.arange(n_agg + 1))
+    rows, cols, vals = [], [], []
+    Bc = np.zeros((k * n_agg, k))
+    dead = []
+    for g in range(n_agg):
+        nodes = order[bounds[g]:bounds[g + 1]]
+        dofs = (bs * nodes[:, None] + np.arange(bs)[None, :]).ravel()
+        Q, R = householder_qr(B[dofs, :])
+        Bc[k * g:k * (g + 1), :] = R
+        rows.append(np.repeat(dofs, k))
+        cols.append(np.tile(k * g + np.arange(k), len(dofs)))
+        vals.append(Q.ravel())
+        if len(dofs) < k:
+            dead += [k * g + c for c in range(len(dofs), k)]
+    P0 = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, k * n_agg))
+    P0.sort_indices()
+    return _as64(P0), Bc, np.asarray(dead, dtype=np.int64)
+
+
+def node_graph(A, bs):
+    """Pattern of the bs x bs blocks of A as a node-level boolean CSR."""
+    A = A.tocsr()
+    n = A.shape[0] // bs
+    rows = np.repeat(np.arange(A.shape[0], dtype=np.int64), np.diff(A.indptr)) // bs
+    cols = A.indices // bs
+    N = sp.csr_matrix((np.ones(len(rows), dtype=np.int8), (rows, cols)), shape=(n, n))
+    N.sum_duplicates()
+    N.data[:] = 1
+    N.sort_indices()
+    return N
 
 
 def _as64(A):
@@ -342,6 +510,10 @@ def build_global_hierarchy(A, owner, nparts, opts=None):
     levels = []
     A = _as64(A)
     owner = np.asarray(owner, dtype=np.int32)
+    bs = int(o["block_size"])
+    B = None if o["nullspace"] is None else np.array(o["nullspace"], dtype=np.float64)
+    if bs > 1 and B is None:
+        raise NotImplementedError("block_size > 1 needs a near-nullspace")
     while True:
         n = A.shape[0]
         lev = dict(A=A, owner=owner)
@@ -349,12 +521,31 @@ def build_global_hierarchy(A, owner, nparts, opts=None):
         if n <= o["coarse_size"] or len(levels) >= o["max_levels"]:
             break
         eps_l = o["eps_strength"] * (0.5 ** (len(levels) - 1))  # Vanek: eps_l = eps * 2^-l
-        S = strength_graph(A, owner, eps_l)
-        agg, counts, agg_loc = aggregate_parts(S, owner, nparts)
-        nc = int(counts.sum())
-        if nc >= n:  # no coarsening possible
-            break
-        P0 = sp.csr_matrix((np.ones(n), (np.arange(n, dtype=np.int64), agg)), shape=(n, nc))
+        dead = np.zeros(0, dtype=np.int64)
+        if B is None:
+            S = strength_graph(A, owner, eps_l)
+            agg, counts, agg_loc = aggregate_parts(S, owner, nparts)
+            nc = int(counts.sum())
+            if nc >= n:  # no coarsening possible
+                break
+            P0 = sp.csr_matrix((np.ones(n), (np.arange(n, dtype=np.int64), agg)), shape=(n, nc))
+            kdof = 1
+        else:
+            # nodes (bs DOFs each) are aggregated on the block pattern; tentative P by per-aggregate QR of B
+            if eps_l > 0.0:
+                raise NotImplementedError("block strength thresholds are not defined: use eps_strength = 0")
+            kdof = B.shape[1]
+            owner_node = owner[::bs]
+            assert np.array_equal(np.repeat(owner_node, bs), owner), "a node's DOFs must share one owner"
+            S = strength_graph(node_graph(A, bs), owner_node, 0.0)
+            agg_node, counts, agg_loc_node = aggregate_parts(S, owner_node, nparts)
+            nagg = int(counts.sum())
+            nc = kdof * nagg
+            if nc >= n:
+                break
+            P0, Bc, dead = tentative_from_nullspace(B, agg_node, nagg, bs)
+            agg = np.repeat(kdof * agg_node, bs)
+            agg_loc = np.repeat(agg_loc_node, bs)
         mask = filter_strength_mask(A, eps_l)
         rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(A.indptr))
         if mask.all():
@@ -376,18 +567,28 @@ def build_global_hierarchy(A, owner, nparts, opts=None):
         omega_p = 4.0 / (3.0 * rho)
         AP0 = spgemm_structural(A_F, _as64(P0))
         ap_rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(AP0.indptr))
+        P0 = _as64(P0)
+        p0_rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(P0.indptr))
         Pc = sp.coo_matrix(
-            (np.concatenate([np.ones(n), -(omega_p * dinv[ap_rows]) * AP0.data]),
-             (np.concatenate([np.arange(n, dtype=np.int64), ap_rows]),
-              np.concatenate([agg, AP0.indices]))), shape=(n, nc)).tocsr()
+            (np.concatenate([P0.data, -(omega_p * dinv[ap_rows]) * AP0.data]),
+             (np.concatenate([p0_rows, ap_rows]),
+              np.concatenate([P0.indices, AP0.indices]))), shape=(n, nc)).tocsr()
         Pc.sort_indices()
         P = _as64(Pc)
         R = transpose_csr(P)
         AP = spgemm_structural(A, P)
         Ac = spgemm_structural(R, AP)
-        coarse_owner = np.repeat(np.arange(nparts, dtype=np.int32), counts)
-        lev.update(agg=agg, agg_local=agg_loc, agg_counts=counts, P=P, R=R, rho=rho, omega_p=omega_p)
+        if len(dead):  # coarse DOFs of aggregates with fewer rows than near-nullspace vectors: empty column
+            Ac = Ac.tolil()
+            for g in dead:
+                Ac[g, g] = 1.0
+            Ac = _as64(Ac.tocsr())
+            Ac.sort_indices()
+        coarse_owner = np.repeat(np.arange(nparts, dtype=np.int32), counts * kdof)
+        lev.update(agg=agg, agg_local=agg_loc, agg_counts=counts, P=P, R=R, rho=rho, omega_p=omega_p, dead=dead)
         A, owner = Ac, coarse_owner
+        if B is not None:
+            B, bs = Bc, kdof
     Ainv = np.linalg.inv(levels[-1]["A"].toarray())
     return dict(levels=levels, coarse_inv=Ainv, opts=o, nparts=nparts)
 

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "pamg_set_matrix_global": [_ctx, C.c_int64, _i64p, _i64p, _f64p, _i32p],
     "pamg_gallery_poisson": [_ctx, C.c_int32, _i64p, _i32p],
     "pamg_gallery_diffusion_jump": [_ctx, C.c_int32, _i64p, _i32p, C.c_int32, C.c_double, C.c_double],
+    "pamg_gallery_elasticity": [_ctx, _i64p, _i32p, C.c_double, C.c_double],
+    "pamg_set_near_nullspace": [_ctx, C.c_int32, C.c_int32, _f64p],
+    "pamg_get_near_nullspace": [_ctx, _i32p, _i32p, _f64p],
     "pamg_uniform_partition": [C.c_int32, _i64p, _i32p, _i32p],
     "pamg_host_matvec_global": [_ctx, _f64p, _f64p],
     "pamg_global_size": [_ctx, _i64p, _i64p],
@@ -195,6 +198,28 @@ class Context:
         p = _as(parts_per_dir, np.int32)
         self._ck(self.lib.pamg_gallery_diffusion_jump(self._h, len(n), _ptr(n, C.c_int64), _ptr(p, C.c_int32),
                                                       int(blocks), float(kmax), float(eps_z)))
+
+    def gallery_elasticity(self, nodes_per_dir, parts_per_dir, E=1.0, nu=0.25):
+        n = _as(nodes_per_dir, np.int64)
+        p = _as(parts_per_dir, np.int32)
+        assert len(n) == 3 and len(p) == 3
+        self._ck(self.lib.pamg_gallery_elasticity(self._h, _ptr(n, C.c_int64), _ptr(p, C.c_int32), float(E), float(nu)))
+
+    def set_near_nullspace(self, block_size, B):
+        if B is None:
+            self._ck(self.lib.pamg_set_near_nullspace(self._h, 1, 0, None))
+            return
+        B = _as(B, np.float64)
+        self._ck(self.lib.pamg_set_near_nullspace(self._h, int(block_size), B.shape[1], _ptr(B, C.c_double)))
+
+    def near_nullspace(self):
+        bs, k = C.c_int32(), C.c_int32()
+        self._ck(self.lib.pamg_get_near_nullspace(self._h, C.byref(bs), C.byref(k), None))
+        n, _ = self.global_size()
+        B = np.zeros((n, max(k.value, 0)))
+        if k.value > 0:
+            self._ck(self.lib.pamg_get_near_nullspace(self._h, C.byref(bs), C.byref(k), _ptr(B, C.c_double)))
+        return bs.value, B
 
     def set_matrix_global(self, indptr, indices, data, owner):
         ip, ix, d, ow = _as(indptr, np.int64), _as(indices, np.int64), _as(data, np.float64), _as(owner, np.int32)

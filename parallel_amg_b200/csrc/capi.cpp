@@ -19,6 +19,8 @@ struct pamg_ctx {
   Csr A;                       // global matrix (host)
   std::vector<int32_t> owner;  // owner[gid]
   bool have_matrix = false;
+  int32_t block_size = 1, ns_k = 0;   // DOFs per node / near-nullspace vectors (0: scalar smoothed aggregation)
+  std::vector<double> nullspace;      // row-major n x ns_k
   std::vector<char> part_set;
   // rows staged by pamg_set_part_rows until all parts are in
   struct PartRows {
@@ -298,7 +300,59 @@ int pamg_setup(pamg_ctx* c, const pamg_options* o) {
     need(opt.nu_pre >= 0 && opt.nu_post >= 0 && opt.nu_pre + opt.nu_post >= 0, "bad sweep counts");
     need(opt.smoother >= 0 && opt.smoother <= 2, "bad smoother");
     c->eng.reset();
-    build_hierarchy(c->A, c->owner, c->nparts, opt, c->h);
+    if (c->ns_k > 0) need((int64_t)c->nullspace.size() == c->A.nrows * c->ns_k, "near-nullspace does not match the matrix");
+    build_hierarchy(c->A, c->owner, c->nparts, opt, c->h, c->block_size, c->ns_k, c->ns_k > 0 ? &c->nullspace : nullptr);
+    return PAMG_OK;
+  });
+}
+
+int pamg_set_near_nullspace(pamg_ctx* c, int32_t block_size, int32_t k, const double* B) {
+  return guard(c, [&] {
+    need(c->have_matrix, "set the matrix first");
+    if (k <= 0 || !B) {  // back to scalar smoothed aggregation
+      c->block_size = 1;
+      c->ns_k = 0;
+      c->nullspace.clear();
+      return PAMG_OK;
+    }
+    need(block_size >= 1 && k <= 64 && c->A.nrows % block_size == 0, "bad block size / vector count");
+    c->block_size = block_size;
+    c->ns_k = k;
+    c->nullspace.assign(B, B + (size_t)c->A.nrows * k);
+    return PAMG_OK;
+  });
+}
+
+int pamg_gallery_elasticity(pamg_ctx* c, const int64_t* nodes_per_dir, const int32_t* parts_per_dir, double E, double nu) {
+  return guard(c, [&] {
+    need(nodes_per_dir && parts_per_dir, "bad arguments");
+    int64_t np = 1;
+    for (int a = 0; a < 3; ++a) {
+      need(nodes_per_dir[a] >= 1 && parts_per_dir[a] >= 1 && parts_per_dir[a] <= nodes_per_dir[a], "bad grid/partition");
+      np *= parts_per_dir[a];
+    }
+    need(np == c->nparts, "prod(parts_per_dir) != nparts");
+    need(E > 0.0 && nu > -1.0 && nu < 0.5, "bad material constants");
+    std::vector<double> coords;
+    gallery_elasticity(nodes_per_dir, E, nu, c->A, coords);
+    std::vector<int32_t> node_owner;
+    uniform_partition(3, nodes_per_dir, parts_per_dir, node_owner);
+    c->owner.resize(node_owner.size() * 3);
+    for (size_t v = 0; v < node_owner.size(); ++v) c->owner[3 * v] = c->owner[3 * v + 1] = c->owner[3 * v + 2] = node_owner[v];
+    rigid_body_modes(coords, c->nullspace);
+    c->block_size = 3;
+    c->ns_k = 6;
+    c->have_matrix = true;
+    return PAMG_OK;
+  });
+}
+
+int pamg_get_near_nullspace(pamg_ctx* c, int32_t* block_size, int32_t* k, double* B /* may be NULL */) {
+  return guard(c, [&] {
+    need(block_size && k, "null output");
+    *block_size = c->block_size;
+    *k = c->ns_k;
+    if (B && c->ns_k > 0) std::memcpy(B, c->nullspace.data(), c->nullspace.size() * sizeof(double));
     return PAMG_OK;
   });
 }

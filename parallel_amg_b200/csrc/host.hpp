@@ -74,8 +74,13 @@ void matvec(const Csr& A, const double* x, double* y);
 // ---- setup ------------------------------------------------------------------------------------
 // Builds every level (global matrices internally, then the per-part split format).
 // Throws std::runtime_error on bad input; the C ABI catches.
+// block_size / ns_k / nullspace: DOFs per node on level 0 and the near-nullspace (row-major n x ns_k, e.g. the
+// 6 rigid-body modes); nullspace == nullptr: scalar smoothed aggregation (piecewise-constant tentative P)
 void build_hierarchy(const Csr& A, const std::vector<int32_t>& owner, int32_t nparts,
-                     const pamg_options& o, Hierarchy& h);
+                     const pamg_options& o, Hierarchy& h, int32_t block_size = 1, int32_t ns_k = 0,
+                     const std::vector<double>* nullspace = nullptr);
+void gallery_elasticity(const int64_t* dims, double E, double nu, Csr& A, std::vector<double>& coords);
+void rigid_body_modes(const std::vector<double>& coords, std::vector<double>& B);
 // halo plans from the index maps of all parts of a level (also used for external hierarchies)
 void build_halo_plans(Level& lev, int32_t nparts);
 void finalize_external(Hierarchy& h);

@@ -139,6 +139,111 @@ void gallery_diffusion_jump(int ndim, const int64_t* dims, int blocks, double km
   });
 }
 
+
+// 3-D linear elasticity, Q1 hexahedra on unit cubes (oracle/amg_oracle.py elasticity_q1): nx x ny x nz FREE
+// nodes, 3 DOFs each (gid = 3 node + component); the node layer at i = -1 is clamped and eliminated.
+// Entries are (lam * sum NL + mu * sum NM) / 72 with integer element sums, hence bit-identical to the oracle.
+void gallery_elasticity(const int64_t* dims, double E, double nu, Csr& A, std::vector<double>& coords) {
+  const int64_t nx = dims[0], ny = dims[1], nz = dims[2];
+  if (nx < 1 || ny < 2 || nz < 2) throw std::runtime_error("elasticity gallery needs nx >= 1, ny >= 2, nz >= 2");
+  const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+  const double mu = E / (2.0 * (1.0 + nu));
+  int G[8][8][3][3];
+  for (int a = 0; a < 8; ++a)
+    for (int b = 0; b < 8; ++b) {
+      const int ab[3] = {a & 1, (a >> 1) & 1, (a >> 2) & 1}, bb[3] = {b & 1, (b >> 1) & 1, (b >> 2) & 1};
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+          int v;
+          if (d == e) {
+            v = (2 * ab[d] - 1) * (2 * bb[d] - 1) * 2;
+            for (int m = 0; m < 3; ++m)
+              if (m != d) v *= (ab[m] == bb[m]) ? 2 : 1;
+          } else {
+            const int m = 3 - d - e;
+            v = (2 * ab[d] - 1) * (2 * bb[e] - 1) * ((ab[m] == bb[m]) ? 6 : 3);
+          }
+          G[a][b][d][e] = v;
+        }
+    }
+  const int64_t nn = nx * ny * nz, n = 3 * nn;
+  A.nrows = A.ncols = n;
+  A.ptr.assign(n + 1, 0);
+  coords.resize(3 * nn);
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < nn; ++v) {
+    const int64_t i = v % nx, j = (v / nx) % ny, k = v / (nx * ny);
+    coords[3 * v] = (double)(i + 1);
+    coords[3 * v + 1] = (double)j;
+    coords[3 * v + 2] = (double)k;
+    int64_t cnt = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+          if (i + dx >= 0 && i + dx < nx && j + dy >= 0 && j + dy < ny && k + dz >= 0 && k + dz < nz) ++cnt;
+    for (int d = 0; d < 3; ++d) A.ptr[3 * v + d + 1] = 3 * cnt;
+  }
+  for (int64_t r = 0; r < n; ++r) A.ptr[r + 1] += A.ptr[r];
+  A.col.resize(A.ptr[n]);
+  A.val.resize(A.ptr[n]);
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < nn; ++v) {
+    const int64_t i = v % nx, j = (v / nx) % ny, k = v / (nx * ny);
+    int64_t q[3] = {A.ptr[3 * v], A.ptr[3 * v + 1], A.ptr[3 * v + 2]};
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int64_t i2 = i + dx, j2 = j + dy, k2 = k + dz;
+          if (i2 < 0 || i2 >= nx || j2 < 0 || j2 >= ny || k2 < 0 || k2 >= nz) continue;
+          const int64_t u = i2 + nx * (j2 + ny * k2);
+          long long nl[3][3] = {{0}}, nm[3][3] = {{0}};
+          for (int64_t cz = std::max(k, k2) - 1; cz <= std::min(k, k2); ++cz) {
+            if (cz < 0 || cz > nz - 2) continue;
+            for (int64_t cy = std::max(j, j2) - 1; cy <= std::min(j, j2); ++cy) {
+              if (cy < 0 || cy > ny - 2) continue;
+              for (int64_t cx = std::max(i, i2) - 1; cx <= std::min(i, i2); ++cx) {
+                if (cx < -1 || cx > nx - 2) continue;
+                const int a = (int)((i - cx) + 2 * (j - cy) + 4 * (k - cz));
+                const int b = (int)((i2 - cx) + 2 * (j2 - cy) + 4 * (k2 - cz));
+                for (int d = 0; d < 3; ++d)
+                  for (int e = 0; e < 3; ++e) {
+                    nl[d][e] += G[a][b][d][e];
+                    nm[d][e] += G[a][b][e][d];
+                    if (d == e) nm[d][e] += G[a][b][0][0] + G[a][b][1][1] + G[a][b][2][2];
+                  }
+              }
+            }
+          }
+          for (int d = 0; d < 3; ++d)
+            for (int e = 0; e < 3; ++e) {
+              A.col[q[d]] = 3 * u + e;
+              A.val[q[d]++] = (lam * (double)nl[d][e] + mu * (double)nm[d][e]) / 72.0;
+            }
+        }
+  }
+}
+
+// rigid-body modes (3 translations, 3 rotations about the axes through the origin), row-major (3 nn) x 6
+void rigid_body_modes(const std::vector<double>& coords, std::vector<double>& B) {
+  const int64_t nn = (int64_t)coords.size() / 3;
+  B.assign((size_t)(18 * nn), 0.0);
+  for (int64_t v = 0; v < nn; ++v) {
+    const double x = coords[3 * v], y = coords[3 * v + 1], z = coords[3 * v + 2];
+    double* r0 = &B[(size_t)(3 * v) * 6];
+    double* r1 = r0 + 6;
+    double* r2 = r1 + 6;
+    r0[0] = 1.0;
+    r1[1] = 1.0;
+    r2[2] = 1.0;
+    r1[3] = -z;
+    r2[3] = y;
+    r0[4] = z;
+    r2[4] = -x;
+    r0[5] = -y;
+    r1[5] = x;
+  }
+}
+
 void matvec(const Csr& A, const double* x, double* y) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < A.nrows; ++i) {
@@ -317,7 +422,9 @@ static int64_t aggregate_part(const Csr& A, const std::vector<int32_t>& owner, c
 // ------------------------------------------------------------------------------------------
 // smoothed prolongator P = (I - w D_F^-1 A_F) P0, w = 4/(3 rho_F)       (App. B items 3-4)
 // ------------------------------------------------------------------------------------------
-static void build_prolongator(const Csr& A, const std::vector<int64_t>& agg_gid, int64_t nc, double eps,
+// P0: tentative prolongator (n x nc, sorted columns): one unit entry per row for scalar problems, the
+// per-aggregate Q factors of the near-nullspace for block problems.
+static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double eps,
                               const std::vector<double>& absdiag, Csr& P, double* omega_out) {
   const int64_t n = A.nrows;
   // filtered matrix A_F (weak off-diagonals lumped into the diagonal); eps == 0 => A_F = A
@@ -391,37 +498,42 @@ static void build_prolongator(const Csr& A, const std::vector<int64_t>& agg_gid,
     std::vector<std::pair<int64_t, double>> acc;
     for (int64_t i = r0; i < r1; ++i) {
       acc.clear();
-      for (int64_t k = F->ptr[i]; k < F->ptr[i + 1]; ++k) acc.emplace_back(agg_gid[F->col[k]], F->val[k]);
+      for (int64_t k = F->ptr[i]; k < F->ptr[i + 1]; ++k) {
+        const int64_t j = F->col[k];
+        const double f = F->val[k];
+        for (int64_t kb = P0.ptr[j]; kb < P0.ptr[j + 1]; ++kb) acc.emplace_back(P0.col[kb], f * P0.val[kb]);
+      }
       std::stable_sort(acc.begin(), acc.end(),
                        [](const std::pair<int64_t, double>& x, const std::pair<int64_t, double>& y) { return x.first < y.first; });
       const double w = -(omega * dinv[i]);
-      const int64_t ci = agg_gid[i];
-      bool placed = false;
+      int64_t pk = P0.ptr[i];  // next tentative entry of this row still to be placed
+      const int64_t pe = P0.ptr[i + 1];
       int64_t cnt = 0;
       for (size_t q = 0; q < acc.size();) {
         const int64_t c = acc[q].first;
         double s = acc[q].second;
         size_t e = q + 1;
         while (e < acc.size() && acc[e].first == c) s += acc[e++].second;
-        if (!placed && ci < c) {  // tentative entry without an A_F P0 partner (no stored diagonal)
-          tcol[t].push_back(ci);
-          tval[t].push_back(1.0);
+        while (pk < pe && P0.col[pk] < c) {  // tentative entries without an A_F P0 partner
+          tcol[t].push_back(P0.col[pk]);
+          tval[t].push_back(P0.val[pk]);
+          ++pk;
           ++cnt;
-          placed = true;
         }
         double v = w * s;
-        if (c == ci) {
-          v = 1.0 + v;
-          placed = true;
+        if (pk < pe && P0.col[pk] == c) {
+          v = P0.val[pk] + v;
+          ++pk;
         }
         tcol[t].push_back(c);
         tval[t].push_back(v);
         ++cnt;
         q = e;
       }
-      if (!placed) {
-        tcol[t].push_back(ci);
-        tval[t].push_back(1.0);
+      while (pk < pe) {
+        tcol[t].push_back(P0.col[pk]);
+        tval[t].push_back(P0.val[pk]);
+        ++pk;
         ++cnt;
       }
       P.ptr[i + 1] = cnt;
@@ -437,6 +549,136 @@ static void build_prolongator(const Csr& A, const std::vector<int64_t>& agg_gid,
     std::copy(tcol[t].begin(), tcol[t].end(), P.col.begin() + P.ptr[r0]);
     std::copy(tval[t].begin(), tval[t].end(), P.val.begin() + P.ptr[r0]);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// near-nullspace tentative prolongator (oracle/amg_oracle.py householder_qr / tentative_from_nullspace)
+// ------------------------------------------------------------------------------------------
+// Thin Householder QR of the m x k row-major block W (overwritten): Q (m x k, row-major) and R (k x k).
+// diag(R) >= 0; a sub-column whose norm is <= 1e-12 of the original column's norm counts as zero (no
+// reflector); m < k pads Q with zero columns and R with zero rows.
+static void householder_qr(std::vector<double>& W, int64_t m, int k, std::vector<double>& Q, std::vector<double>& R) {
+  const int r = (int)std::min<int64_t>(m, k);
+  std::vector<double> cn(k, 0.0);
+  for (int j = 0; j < k; ++j) {
+    double s = 0.0;
+    for (int64_t i = 0; i < m; ++i) s += W[i * k + j] * W[i * k + j];
+    cn[j] = std::sqrt(s);
+  }
+  std::vector<std::vector<double>> V(r);
+  std::vector<double> vn2(r, 0.0);
+  for (int j = 0; j < r; ++j) {
+    double s = 0.0;
+    for (int64_t i = j; i < m; ++i) s += W[i * k + j] * W[i * k + j];
+    const double alpha = std::sqrt(s);
+    if (alpha <= 1e-12 * cn[j] || cn[j] == 0.0) {
+      for (int64_t i = j; i < m; ++i) W[i * k + j] = 0.0;
+      continue;  // V[j] stays empty: H_j = I
+    }
+    std::vector<double>& v = V[j];
+    v.resize(m - j);
+    for (int64_t i = j; i < m; ++i) v[i - j] = W[i * k + j];
+    const double beta = v[0] >= 0.0 ? -alpha : alpha;
+    v[0] -= beta;
+    double n2 = 0.0;
+    for (double t : v) n2 += t * t;
+    vn2[j] = n2;
+    for (int c = j; c < k; ++c) {
+      double dot = 0.0;
+      for (int64_t i = j; i < m; ++i) dot += v[i - j] * W[i * k + c];
+      const double f = (2.0 / n2) * dot;
+      for (int64_t i = j; i < m; ++i) W[i * k + c] -= v[i - j] * f;
+    }
+    for (int64_t i = j + 1; i < m; ++i) W[i * k + j] = 0.0;
+  }
+  R.assign((size_t)k * k, 0.0);
+  for (int i = 0; i < r; ++i)
+    for (int c = i; c < k; ++c) R[(size_t)i * k + c] = W[(size_t)i * k + c];
+  Q.assign((size_t)m * k, 0.0);
+  for (int i = 0; i < r; ++i) Q[(size_t)i * k + i] = 1.0;
+  for (int j = r - 1; j >= 0; --j) {
+    if (V[j].empty()) continue;
+    const std::vector<double>& v = V[j];
+    for (int c = 0; c < r; ++c) {
+      double dot = 0.0;
+      for (int64_t i = j; i < m; ++i) dot += v[i - j] * Q[i * k + c];
+      const double f = (2.0 / vn2[j]) * dot;
+      for (int64_t i = j; i < m; ++i) Q[i * k + c] -= v[i - j] * f;
+    }
+  }
+  for (int j = 0; j < r; ++j)
+    if (R[(size_t)j * k + j] < 0.0) {
+      for (int c = 0; c < k; ++c) R[(size_t)j * k + c] = -R[(size_t)j * k + c];
+      for (int64_t i = 0; i < m; ++i) Q[i * k + j] = -Q[i * k + j];
+    }
+}
+
+// P0 (n x k n_agg; every row of an aggregate stores all k entries), coarse near-nullspace Bc (k n_agg x k)
+// and the coarse DOFs whose column is empty (aggregates with fewer rows than k)
+static void tentative_from_nullspace(const std::vector<double>& B, int k, int bs, const std::vector<int64_t>& agg_node,
+                                     int64_t n_agg, Csr& P0, std::vector<double>& Bc, std::vector<int64_t>& dead) {
+  const int64_t nn = (int64_t)agg_node.size(), n = nn * bs;
+  std::vector<int64_t> start(n_agg + 1, 0);
+  for (int64_t v = 0; v < nn; ++v) start[agg_node[v] + 1]++;
+  for (int64_t g = 0; g < n_agg; ++g) start[g + 1] += start[g];
+  std::vector<int64_t> members(nn), pos(start.begin(), start.end() - 1);
+  for (int64_t v = 0; v < nn; ++v) members[pos[agg_node[v]]++] = v;  // ascending node id inside each aggregate
+  P0.nrows = n;
+  P0.ncols = k * n_agg;
+  P0.ptr.resize(n + 1);
+  for (int64_t i = 0; i <= n; ++i) P0.ptr[i] = i * k;
+  P0.col.resize((size_t)n * k);
+  P0.val.resize((size_t)n * k);
+  Bc.assign((size_t)n_agg * k * k, 0.0);
+  dead.clear();
+  std::vector<char> is_dead((size_t)n_agg * k, 0);
+#pragma omp parallel
+  {
+    std::vector<double> W, Q, R;
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t g = 0; g < n_agg; ++g) {
+      const int64_t m = (start[g + 1] - start[g]) * bs;
+      W.resize((size_t)m * k);
+      for (int64_t a = start[g]; a < start[g + 1]; ++a)
+        for (int d = 0; d < bs; ++d) {
+          const int64_t dof = members[a] * bs + d, row = (a - start[g]) * bs + d;
+          for (int c = 0; c < k; ++c) W[(size_t)row * k + c] = B[(size_t)dof * k + c];
+        }
+      householder_qr(W, m, k, Q, R);
+      for (int c = 0; c < k * k; ++c) Bc[(size_t)g * k * k + c] = R[c];
+      for (int64_t a = start[g]; a < start[g + 1]; ++a)
+        for (int d = 0; d < bs; ++d) {
+          const int64_t dof = members[a] * bs + d, row = (a - start[g]) * bs + d;
+          for (int c = 0; c < k; ++c) {
+            P0.col[(size_t)dof * k + c] = g * k + c;
+            P0.val[(size_t)dof * k + c] = Q[(size_t)row * k + c];
+          }
+        }
+      for (int64_t c = m; c < k; ++c) is_dead[(size_t)g * k + c] = 1;
+    }
+  }
+  for (int64_t c = 0; c < n_agg * k; ++c)
+    if (is_dead[c]) dead.push_back(c);
+}
+
+// pattern of the bs x bs blocks of A as a node-level matrix (values unused)
+static void node_graph(const Csr& A, int bs, Csr& N) {
+  const int64_t nn = A.nrows / bs;
+  N.nrows = N.ncols = nn;
+  N.ptr.assign(nn + 1, 0);
+  std::vector<std::vector<int64_t>> rows(nn);
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < nn; ++v) {
+    std::vector<int64_t>& r = rows[v];
+    for (int d = 0; d < bs; ++d)
+      for (int64_t k = A.ptr[v * bs + d]; k < A.ptr[v * bs + d + 1]; ++k) r.push_back(A.col[k] / bs);
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+  }
+  for (int64_t v = 0; v < nn; ++v) N.ptr[v + 1] = N.ptr[v] + (int64_t)rows[v].size();
+  N.col.resize(N.ptr[nn]);
+  N.val.assign(N.ptr[nn], 1.0);
+  for (int64_t v = 0; v < nn; ++v) std::copy(rows[v].begin(), rows[v].end(), N.col.begin() + N.ptr[v]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -614,8 +856,17 @@ static void fill_diag(PartLevel& pl) {
 // ------------------------------------------------------------------------------------------
 // whole setup
 // ------------------------------------------------------------------------------------------
-void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t nparts, const pamg_options& o, Hierarchy& h) {
+void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t nparts, const pamg_options& o, Hierarchy& h,
+                     int32_t block_size, int32_t ns_k, const std::vector<double>* nullspace) {
   if (A0.nrows != (int64_t)owner0.size()) throw std::runtime_error("owner size mismatch");
+  const bool use_ns = nullspace && ns_k > 0;
+  if (block_size < 1) block_size = 1;
+  if (block_size > 1 && !use_ns) throw std::runtime_error("block_size > 1 needs a near-nullspace (pamg_set_near_nullspace)");
+  if (use_ns && ((int64_t)nullspace->size() != A0.nrows * ns_k || A0.nrows % block_size))
+    throw std::runtime_error("near-nullspace / block size do not match the matrix");
+  std::vector<double> Bcur;  // near-nullspace of the current level (row-major n x ns_k)
+  if (use_ns) Bcur = *nullspace;
+  int bs = block_size;
   h = Hierarchy();
   h.nparts = nparts;
   h.opts = o;
@@ -647,22 +898,65 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
 
     std::vector<std::vector<int32_t>> aggs(nparts);
     std::vector<int64_t> counts(nparts, 0);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int32_t p = 0; p < nparts; ++p) counts[p] = aggregate_part(cur.A, cur.owner, cur.oi, p, eps, absdiag, aggs[p]);
     std::vector<int64_t> off(nparts + 1, 0);
-    for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
-    const int64_t nc = off[nparts];
-    if (nc >= n) break;
-    std::vector<int64_t> agg_gid(n);
+    Csr P0;
+    std::vector<int64_t> dead;
+    std::vector<double> Bc;
+    int64_t nc = 0;
+    int kdof = 1;
     cur.agg_loc.resize(n);
-    for (int32_t p = 0; p < nparts; ++p) {
-      const auto& own = cur.oi.own[p];
-      for (size_t li = 0; li < own.size(); ++li) {
-        cur.agg_loc[own[li]] = aggs[p][li];
-        agg_gid[own[li]] = off[p] + aggs[p][li];
+    if (!use_ns) {
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int32_t p = 0; p < nparts; ++p) counts[p] = aggregate_part(cur.A, cur.owner, cur.oi, p, eps, absdiag, aggs[p]);
+      for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
+      nc = off[nparts];
+      if (nc >= n) break;
+      P0.nrows = n;
+      P0.ncols = nc;
+      P0.ptr.resize(n + 1);
+      P0.col.resize(n);
+      P0.val.assign(n, 1.0);
+      for (int64_t i = 0; i <= n; ++i) P0.ptr[i] = i;
+      for (int32_t p = 0; p < nparts; ++p) {
+        const auto& own = cur.oi.own[p];
+        for (size_t li = 0; li < own.size(); ++li) {
+          cur.agg_loc[own[li]] = aggs[p][li];
+          P0.col[own[li]] = off[p] + aggs[p][li];
+        }
       }
+    } else {
+      // nodes (bs DOFs each) are aggregated on the block pattern; tentative P by per-aggregate QR of B
+      if (eps > 0.0) throw std::runtime_error("block strength thresholds are not defined: use eps_strength = 0");
+      kdof = ns_k;
+      const int64_t nn = n / bs;
+      std::vector<int32_t> owner_node(nn);
+      for (int64_t v = 0; v < nn; ++v) {
+        owner_node[v] = cur.owner[v * bs];
+        for (int d = 1; d < bs; ++d)
+          if (cur.owner[v * bs + d] != owner_node[v]) throw std::runtime_error("the DOFs of a node must share one owner");
+      }
+      Csr N;
+      node_graph(cur.A, bs, N);
+      OwnIndex oin;
+      build_own_index(owner_node, nparts, oin);
+      std::vector<double> none;
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int32_t p = 0; p < nparts; ++p) counts[p] = aggregate_part(N, owner_node, oin, p, 0.0, none, aggs[p]);
+      for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
+      const int64_t nagg = off[nparts];
+      nc = nagg * kdof;
+      if (nc >= n) break;
+      std::vector<int64_t> agg_node(nn);
+      for (int32_t p = 0; p < nparts; ++p) {
+        const auto& own = oin.own[p];
+        for (size_t li = 0; li < own.size(); ++li) {
+          agg_node[own[li]] = off[p] + aggs[p][li];
+          for (int d = 0; d < bs; ++d) cur.agg_loc[own[li] * bs + d] = aggs[p][li];
+        }
+      }
+      tentative_from_nullspace(Bcur, kdof, bs, agg_node, nagg, P0, Bc, dead);
     }
-    build_prolongator(cur.A, agg_gid, nc, eps, absdiag, cur.P, &cur.omega_p);
+    build_prolongator(cur.A, P0, nc, eps, absdiag, cur.P, &cur.omega_p);
     transpose(cur.P, cur.R);
     G nxt;
     {
@@ -670,10 +964,23 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       spgemm(cur.A, cur.P, AP);
       spgemm(cur.R, AP, nxt.A);
     }
+    for (int64_t gd : dead) {  // empty coarse column: unit diagonal keeps the Galerkin matrix regular
+      bool found = false;
+      for (int64_t k = nxt.A.ptr[gd]; k < nxt.A.ptr[gd + 1]; ++k)
+        if (nxt.A.col[k] == gd) {
+          nxt.A.val[k] = 1.0;
+          found = true;
+        }
+      if (!found) throw std::runtime_error("internal: no diagonal slot for an empty coarse column");
+    }
     nxt.owner.resize(nc);
     for (int32_t p = 0; p < nparts; ++p)
-      for (int64_t c = off[p]; c < off[p + 1]; ++c) nxt.owner[c] = p;
+      for (int64_t c = off[p] * kdof; c < off[p + 1] * kdof; ++c) nxt.owner[c] = p;
     g.push_back(std::move(nxt));
+    if (use_ns) {
+      Bcur.swap(Bc);
+      bs = kdof;
+    }
   }
 
   const int32_t L = (int32_t)g.size();

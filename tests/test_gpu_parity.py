@@ -202,6 +202,52 @@ def test_coarse_agglomeration_thresholds(dims, pp, tail_rows):
     assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
 
 
+@pytest.mark.parametrize("dims,pp", [((8, 7, 6), (2, 1, 1)), ((10, 9, 8), (2, 2, 1)), ((7, 6, 6), (1, 1, 1))])
+@pytest.mark.parametrize("fmt", ["auto", "sell2"])
+def test_elasticity_rigid_body_sa_parity(dims, pp, fmt):
+    """BASELINE config 4 at test size: 3-DOF Q1 elasticity with rigid-body near-nullspace SA (27-point node
+    stencil, ~80 nnz/row, 6-DOF coarse nodes).  Device V-cycle and PCG vs the oracle on the oracle-built hierarchy."""
+    nparts = int(np.prod(pp))
+    A, coords = O.elasticity_q1(dims)
+    B = O.rigid_body_modes(coords)
+    owner = np.repeat(O.uniform_partition(pp, dims), 3).astype(np.int32)
+    h = O.build(A, owner, nparts, dict(block_size=3, nullspace=B, coarse_size=60))
+    c = product_context_from_oracle(h, None, **({} if fmt == "auto" else FORMATS[fmt]))
+    c.device_init()
+    lev = h["levels"][0]
+    n = A.shape[0]
+    for l, levl in enumerate(h["levels"]):
+        Al = h["global"]["levels"][l]["A"]
+        x = det_vector(Al.shape[0], 5 + l)
+        assert rel_err(c.spmv(l, own_parts(levl, x)), own_parts(levl, Al @ x)) <= TOL_KERNEL
+    b = det_vector(n, 33)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    rhs = A @ det_vector(n, 34)
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, rhs))
+    x, it, hist, ok = c.pcg(own_parts(lev, rhs))
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
+    assert rel_err(x, own_of(lev, xs)) <= 1e-9
+
+
+def test_elasticity_product_setup_and_solve():
+    """Product path end to end (gallery -> host rigid-body SA -> device PCG) at 24^3 nodes (41k DOFs)."""
+    dims = (24, 24, 24)
+    c = L.Context(2)
+    c.gallery_elasticity(dims, (2, 1, 1))
+    c.setup()
+    c.device_init()
+    n, nnz = c.global_size()
+    b = c.host_matvec_global(det_vector(n, 3))
+    own = [c.index_maps(0, p)[0] for p in range(2)]
+    x, it, hist, ok = c.pcg([b[o] for o in own], rtol=1e-8, maxiter=200)
+    assert ok and it < 60
+    xg = np.zeros(n)
+    for o, xp in zip(own, x):
+        xg[o] = xp
+    assert np.linalg.norm(c.host_matvec_global(xg) - b) <= 1.001e-8 * np.linalg.norm(b)
+
+
 def test_pcg_graph_and_eager_agree_bitwise():
     A, h, c1 = make((20, 20, 20), (2, 2, 2), None, use_graph=1)
     _, _, c0 = make((20, 20, 20), (2, 2, 2), None, use_graph=0)

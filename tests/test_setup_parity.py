@@ -103,6 +103,48 @@ def test_jump_coefficient_gallery_matches_oracle():
     check_structure(c, h)
 
 
+@pytest.mark.parametrize("dims,pp", [((8, 7, 6), (2, 1, 1)), ((9, 8, 7), (2, 2, 1)), ((6, 5, 5), (1, 1, 1)), ((10, 9, 3), (3, 2, 1))])
+def test_elasticity_gallery_and_nullspace_setup_match_oracle(dims, pp):
+    """BASELINE config 4 at test size: Q1 elasticity, 3 DOFs per node, rigid-body near-nullspace.  The gallery
+    (integer element sums) and the rigid-body modes are bit-exact; node aggregates, index maps, halo plans and
+    the structure of every block are bit-exact; values (per-aggregate Householder QR) to 1e-12."""
+    nparts = int(np.prod(pp))
+    A, coords = O.elasticity_q1(dims)
+    B = O.rigid_body_modes(coords)
+    owner = np.repeat(O.uniform_partition(pp, dims), 3).astype(np.int32)
+    c = L.Context(nparts)
+    c.gallery_elasticity(dims, pp)
+    n, nnz = c.global_size()
+    assert (n, nnz) == (A.shape[0], A.nnz)
+    c2 = L.Context(nparts)
+    c2.set_matrix_global(A.indptr, A.indices, A.data, owner)
+    x = np.linspace(-1, 1, n)
+    assert np.array_equal(c.host_matvec_global(x), c2.host_matvec_global(x))
+    bs, Bp = c.near_nullspace()
+    assert bs == 3 and np.array_equal(Bp, B)
+    oopts = dict(block_size=3, nullspace=B, coarse_size=60)
+    h = O.build(A, owner, nparts, oopts)
+    assert len(h["levels"]) >= 2
+    c.setup(c.default_options(coarse_size=60))
+    check_structure(c, h)
+    # the same hierarchy from a caller-supplied matrix + near-nullspace
+    c2.set_near_nullspace(3, B)
+    c2.setup(c2.default_options(coarse_size=60))
+    check_structure(c2, h)
+
+
+def test_near_nullspace_argument_checks():
+    c = L.Context(1)
+    c.gallery_poisson((6, 6), (1, 1))
+    with pytest.raises(L.PamgError):
+        c.set_near_nullspace(5, np.ones((36, 2)))      # 36 rows are not a multiple of 5
+    c.set_near_nullspace(1, np.ones((36, 1)))          # k = 1: normalised piecewise-constant tentative P
+    c.setup(c.default_options(coarse_size=10))
+    assert c.num_levels() >= 2
+    c.set_near_nullspace(1, None)                      # back to scalar SA
+    c.setup(c.default_options(coarse_size=10))
+
+
 def test_uniform_partition_matches_oracle():
     import ctypes as C
     lib = L.load()
