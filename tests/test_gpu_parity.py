@@ -230,6 +230,30 @@ def test_elasticity_rigid_body_sa_parity(dims, pp, fmt):
     assert rel_err(x, own_of(lev, xs)) <= 1e-9
 
 
+@pytest.mark.parametrize("pp", [(2, 2, 2), (1, 1, 1)])
+def test_jump_coefficient_anisotropic_diffusion_parity(pp):
+    """BASELINE config 5 at test size: -div(K grad u), K = diag(k, k, 1e-3 k), k in {1, 1e4} on a checkerboard;
+    strength threshold eps = 0.0831 (weak couplings filtered and lumped).  V-cycle and PCG vs the oracle, with the
+    coarse levels agglomerated (replicated tail) on the multi-part layout."""
+    dims = (16, 16, 16)
+    nparts = int(np.prod(pp))
+    A = O.diffusion_fv(dims, O.jump_coefficient_k(dims, blocks=4, kmax=1e4, eps_z=1e-3))
+    owner = O.uniform_partition(pp, dims)
+    oopts = {"eps_strength": 0.0831}
+    h = O.build(A, owner, nparts, oopts)
+    c = product_context_from_oracle(h, oopts)
+    c.device_init()
+    lev = h["levels"][0]
+    n = A.shape[0]
+    b = det_vector(n, 61)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    rhs = A @ det_vector(n, 62)
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, rhs), maxiter=400)
+    x, it, hist, ok = c.pcg(own_parts(lev, rhs), maxiter=400)
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-6)
+
+
 def test_elasticity_product_setup_and_solve():
     """Product path end to end (gallery -> host rigid-body SA -> device PCG) at 24^3 nodes (41k DOFs)."""
     dims = (24, 24, 24)
