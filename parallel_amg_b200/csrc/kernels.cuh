@@ -685,7 +685,8 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
   constexpr int U = RPT == 1 ? 8 : 4;  // entries of a row in flight per step
   const int lane = threadIdx.x & 31;
   const int wpb = BLOCK / 32;
-  double acc = 0.0;
+  __shared__ double s_acc[DOT ? BLOCK : 1];  // per-thread running dot (each thread touches only its own slot)
+  if (DOT) s_acc[threadIdx.x] = 0.0;
   for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
     const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
     const int slot0 = sl * (32 * RPT) + lane * RPT;
@@ -743,9 +744,9 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
         if (DOT) contrib += res;
       }
     }
-    if (DOT) acc += contrib;
+    if (DOT) s_acc[threadIdx.x] += contrib;  // in shared memory: a register live across the entry loop costs its load batching
   }
-  if (DOT) dot_finish(acc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+  if (DOT) dot_finish(s_acc[threadIdx.x], partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }
 
 // ---------------------------------------------------------------------------------------------

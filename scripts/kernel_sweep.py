@@ -50,7 +50,7 @@ for name, kw in CONFIGS.items():
         it, hist, ok = c.pcg_resident(1e-8, 200, True)
     st = c.stats()
     row = dict(iters=it, solve_ms=st.solve_ms, vcycle_ms=float(np.mean(c.time_kernel(5, 0, 13, False)[3:])))
-    for lvl in range(min(2, c.num_levels() - 1)):
+    for lvl in range(min(int(os.environ.get('SWEEP_LEVELS', '2')), c.num_levels() - 1)):
         info = c.level_info(lvl, 0)
         nr, nc = info.n_own, info.n_own_coarse
         a_b = 12 * info.nnz[0] + 4 * (nr + 1) + 16 * nr
