@@ -33,6 +33,14 @@ WORKLOADS = {
     # BASELINE.json configs[3]: 27-point node stencil, 3 DOFs per node, rigid-body near-nullspace SA
     "elasticity3d-96": dict(dims=(96, 96, 96), kind="elasticity",
                             desc="3D linear elasticity Q1, 96^3 nodes x 3 DOF (2.65M DOF), rigid-body SA, b=A*xstar, x0=0, rtol 1e-8"),
+    # BASELINE.json configs[4] (512^3 on 8 GPUs) and reduced sizes of the same operator: -div(K grad u), K = diag(k,k,1e-3 k),
+    # k in {1, 1e4} on an 8^3 checkerboard; strength threshold 0.08 (without it PCG needs > 400 iterations)
+    "diffusion-jump-3d-512": dict(dims=(512, 512, 512), kind="jump", opts=dict(eps_strength=0.08),
+                                  desc="3D jump-coefficient anisotropic diffusion 512^3 (134M DOF), eps 0.08, b=A*xstar, x0=0, rtol 1e-8"),
+    "diffusion-jump-3d-256": dict(dims=(256, 256, 256), kind="jump", opts=dict(eps_strength=0.08),
+                                  desc="3D jump-coefficient anisotropic diffusion 256^3 (16.7M DOF), eps 0.08, b=A*xstar, x0=0, rtol 1e-8"),
+    "diffusion-jump-3d-128": dict(dims=(128, 128, 128), kind="jump", opts=dict(eps_strength=0.08),
+                                  desc="3D jump-coefficient anisotropic diffusion 128^3 (2.1M DOF), eps 0.08, b=A*xstar, x0=0, rtol 1e-8"),
     "elasticity3d-48": dict(dims=(48, 48, 48), kind="elasticity",
                             desc="3D linear elasticity Q1, 48^3 nodes x 3 DOF (332k DOF), rigid-body SA, b=A*xstar, x0=0, rtol 1e-8"),
 }
@@ -41,6 +49,8 @@ WORKLOADS = {
 def make_problem(c, wl, nparts):
     if wl.get("kind") == "elasticity":
         c.gallery_elasticity(wl["dims"], PARTS[nparts])
+    elif wl.get("kind") == "jump":
+        c.gallery_diffusion_jump(wl["dims"], PARTS[nparts], blocks=8, kmax=1.0e4, eps_z=1.0e-3)
     else:
         c.gallery_poisson(wl["dims"], PARTS[nparts])
 PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
@@ -186,7 +196,7 @@ def run_reference(args, wl, rank, world):
     c = L.Context(nparts)
     dims = wl["dims"]
     make_problem(c, wl, nparts)
-    c.setup()
+    c.setup(c.default_options(**wl.get("opts", {})))
     n, nnz = c.global_size()
     b = c.host_matvec_global(xstar(n))
     b_parts = [b[c.index_maps(0, p)[0]] for p in range(nparts)]
@@ -217,6 +227,7 @@ def main():
     ap.add_argument("--workload", default="poisson3d-256", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--smoother", default="jacobi")
+    ap.add_argument("--replicate-setup", action="store_true", help="N > 1: every rank runs the host setup itself (default: rank 0 builds, the others load it from shared memory)")
     ap.add_argument("--trace", default=None, help="write a per-kernel timeline of one solve (device globaltimer) to this file prefix")
     args = ap.parse_args()
     if args.gpus not in PARTS:
@@ -250,27 +261,55 @@ def main():
 
     nparts = args.gpus
     dims = wl["dims"]
-    L.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))  # torchrun exports OMP_NUM_THREADS=1
+    # Host setup: rank 0 builds the hierarchy once with every host core and hands it to the other ranks through a
+    # shared-memory file (each loads only its own part in full); --replicate-setup repeats it in every rank instead.
+    share = world > 1 and not args.replicate_setup
+    L.set_num_threads((os.cpu_count() or 1) if share else max(1, (os.cpu_count() or 1) // max(world, 1)))  # torchrun exports OMP_NUM_THREADS=1
     c = L.Context(nparts)
     t0 = time.perf_counter()
-    make_problem(c, wl, nparts)
-    # host setup is replicated on every rank (deterministic); run it in waves so that the box's memory
-    # holds the concurrent copies (256^3 needs ~13 GB per process while building)
-    if world > 1:
-        try:
-            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
-        except Exception:
-            avail = 64 << 30
-        need = 1000 * int(np.prod(dims)) * (30 if wl.get("kind") == "elasticity" else 1)  # bytes, generous
-        per_wave = max(1, min(world, int(0.6 * avail // need)))
-        for w0 in range(0, world, per_wave):
-            if w0 <= rank < w0 + per_wave:
-                c.setup(c.default_options())
-            dist.barrier()
+    opts_kw = wl.get("opts", {})
+    if share:
+        import shutil
+        need_bytes = 400 * int(np.prod(dims)) * (12 if wl.get("kind") == "elasticity" else 1)   # generous file-size estimate
+        shm = "/tmp"
+        for cand in ("/dev/shm", "/tmp"):
+            try:
+                if shutil.disk_usage(cand).free > need_bytes:
+                    shm = cand
+                    break
+            except OSError:
+                pass
+        path = os.path.join(shm, f"pamg_hier_{os.environ.get('MASTER_PORT', '0')}_{args.workload}_{world}.bin")
+        meta = [None]
+        if rank == 0:
+            make_problem(c, wl, nparts)
+            c.setup(c.default_options(**opts_kw))
+            c.hierarchy_save(path)
+            meta = [c.global_size()]
+        dist.broadcast_object_list(meta, src=0)
+        n, nnz = meta[0]
+        if rank != 0:
+            c.hierarchy_load(path, keep_part=rank)
+        dist.barrier()
+        if rank == 0:
+            os.remove(path)
     else:
-        c.setup(c.default_options())
+        make_problem(c, wl, nparts)
+        if world > 1:  # replicated setup in waves so that the box's memory holds the concurrent copies
+            try:
+                avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+            except Exception:
+                avail = 64 << 30
+            need = 1000 * int(np.prod(dims)) * (30 if wl.get("kind") == "elasticity" else 1)  # bytes, generous
+            per_wave = max(1, min(world, int(0.6 * avail // need)))
+            for w0 in range(0, world, per_wave):
+                if w0 <= rank < w0 + per_wave:
+                    c.setup(c.default_options(**opts_kw))
+                dist.barrier()
+        else:
+            c.setup(c.default_options(**opts_kw))
+        n, nnz = c.global_size()
     setup_s = time.perf_counter() - t0
-    n, nnz = c.global_size()
     if world > 1:
         c.device_init([rank], [local_rank])
         blobs = [None] * world
@@ -283,8 +322,15 @@ def main():
     else:
         c.device_init([0], [local_rank])
         mine = [0]
+    have_A = (not share) or rank == 0      # only the rank that ran the gallery holds the global matrix
     xs_true = xstar(n)
-    b = c.host_matvec_global(xs_true)
+    if share:  # b = A x* is computed where A lives and broadcast through the GPUs
+        tb = torch.from_numpy(c.host_matvec_global(xs_true)).cuda() if rank == 0 else torch.empty(n, dtype=torch.float64, device="cuda")
+        dist.broadcast(tb, src=0)
+        b = tb.cpu().numpy()
+        del tb
+    else:
+        b = c.host_matvec_global(xs_true)
     own = {p: c.index_maps(0, p)[0] for p in mine}
     # pinned host buffers for the e2e leg (the library copies from/to these pointers)
     b_pin = {p: torch.from_numpy(b[own[p]].copy()).pin_memory() for p in mine}
@@ -321,7 +367,7 @@ def main():
         t = torch.from_numpy(xg).cuda()
         dist.all_reduce(t)
         xg = t.cpu().numpy()
-    true_rel = float(np.linalg.norm(b - c.host_matvec_global(xg)) / np.linalg.norm(b))
+    true_rel = float(np.linalg.norm(b - c.host_matvec_global(xg)) / np.linalg.norm(b)) if have_A else 0.0
     assert true_rel <= 2e-8, f"true residual {true_rel}"
     sol_err = float(np.abs(xg - xs_true).max())
 
@@ -378,7 +424,7 @@ def main():
             config=dict(workload=args.workload, description=wl["desc"], parts=list(PARTS[nparts]), iters=int(it),
                         levels=c.num_levels(), smoother="jacobi(2/3) 1+1", l2="working set >> 126 MB L2 (no flush needed)",
                         timing="CUDA events inside libpamg around each solve, summed over steps, max over ranks",
-                        host_setup_s=round(setup_s, 1)),
+                        host_setup_s=round(setup_s, 1), host_setup="rank 0 + shared-memory hand-off" if share else "every rank"),
             vcycle_ms=float(np.mean(vc)), wall_ms_per_step=wall_ms / args.steps, true_residual_rel=true_rel, solution_max_err=sol_err,
             roofline=dict(bound="hbm", kernel=kname + " level 0: y = A x, fp64 values / int32 columns", achieved=dom["gbs"],
                           peak=peak, unit="GB/s", frac=dom["gbs"] / peak, peak_source=peak_src, traffic=traffic,

@@ -161,6 +161,13 @@ int pamg_level_upload(pamg_ctx* c, int32_t level, int32_t part, int64_t n_own, i
 int pamg_coarse_upload(pamg_ctx* c, int64_t n, const double* inverse_row_major);
 int pamg_hierarchy_end(pamg_ctx* c);
 
+/* One process per GPU: the rank that ran pamg_setup saves the hierarchy (e.g. under /dev/shm) and the other
+ * ranks load it instead of repeating the setup.  keep_part >= 0 loads only that part's matrices in full (plus
+ * every part on the small levels of the replicated coarse tail) and metadata for the rest; keep_part < 0 loads
+ * everything.  The loading context must have been created with the same number of parts. */
+int pamg_hierarchy_save(pamg_ctx* c, const char* path);
+int pamg_hierarchy_load(pamg_ctx* c, const char* path, int32_t keep_part);
+
 /* ---- hierarchy queries (bit-exact parity of maps / aggregates / CSR structure) --------- */
 int pamg_num_levels(pamg_ctx* c, int32_t* n_levels);
 int pamg_get_level_info(pamg_ctx* c, int32_t level, int32_t part, pamg_level_info* info);

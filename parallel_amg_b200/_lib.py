@@ -78,6 +78,8 @@ PROTOTYPES = {
                           _P(_i64p), _P(_i32p), _P(_f64p), C.c_double],
     "pamg_coarse_upload": [_ctx, C.c_int64, _f64p],
     "pamg_hierarchy_end": [_ctx],
+    "pamg_hierarchy_save": [_ctx, C.c_char_p],
+    "pamg_hierarchy_load": [_ctx, C.c_char_p, C.c_int32],
     "pamg_num_levels": [_ctx, _i32p],
     "pamg_get_level_info": [_ctx, C.c_int32, C.c_int32, _P(LevelInfo)],
     "pamg_get_index_maps": [_ctx, C.c_int32, C.c_int32, _i64p, _i64p, _i32p],
@@ -278,6 +280,13 @@ class Context:
         inv = _as(coarse_inv, np.float64)
         self._ck(self.lib.pamg_coarse_upload(self._h, inv.shape[0], _ptr(inv, C.c_double)))
         self._ck(self.lib.pamg_hierarchy_end(self._h))
+
+    def hierarchy_save(self, path):
+        self._ck(self.lib.pamg_hierarchy_save(self._h, str(path).encode()))
+
+    def hierarchy_load(self, path, keep_part=-1):
+        self._info_cache.clear()
+        self._ck(self.lib.pamg_hierarchy_load(self._h, str(path).encode(), int(keep_part)))
 
     # ---- queries ----
     def num_levels(self):

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpamg.so")
 STAMP = os.path.join(HERE, ".libpamg.stamp")
 
-CXX_SOURCES = ["host_setup.cpp", "capi.cpp"]
+CXX_SOURCES = ["host_setup.cpp", "hierarchy_io.cpp", "capi.cpp"]
 CU_SOURCES = ["engine.cu"]
 DEPS = ["host.hpp", "engine.hpp", "kernels.cuh", os.path.join("..", "..", "include", "pamg.h")]
 

@@ -306,6 +306,25 @@ int pamg_setup(pamg_ctx* c, const pamg_options* o) {
   });
 }
 
+int pamg_hierarchy_save(pamg_ctx* c, const char* path) {
+  return guard(c, [&] {
+    need(path != nullptr, "null path");
+    need(c->h.ready, "hierarchy not set up");
+    save_hierarchy(c->h, path);
+    return PAMG_OK;
+  });
+}
+
+int pamg_hierarchy_load(pamg_ctx* c, const char* path, int32_t keep_part) {
+  return guard(c, [&] {
+    need(path != nullptr, "null path");
+    c->eng.reset();
+    load_hierarchy(c->h, path, keep_part);
+    need(c->h.nparts == c->nparts, "hierarchy file was written for a different number of parts");
+    return PAMG_OK;
+  });
+}
+
 int pamg_set_near_nullspace(pamg_ctx* c, int32_t block_size, int32_t k, const double* B) {
   return guard(c, [&] {
     need(c->have_matrix, "set the matrix first");
@@ -463,10 +482,10 @@ int pamg_get_level_info(pamg_ctx* c, int32_t level, int32_t part, pamg_level_inf
     info->n_own = pl.n_own;
     info->n_ghost = pl.n_ghost;
     info->n_own_coarse = pl.n_own_coarse;
-    for (int b = 0; b < 6; ++b) info->nnz[b] = pl.blk[b].nnz();
+    for (int b = 0; b < 6; ++b) info->nnz[b] = pl.block_nnz(b);
     info->n_recv_nbrs = (int32_t)pl.recv.size();
     info->n_send_nbrs = (int32_t)pl.send.size();
-    info->n_send = (int64_t)pl.send_idx.size();
+    info->n_send = pl.n_send_entries();
     info->rho = c->h.levels[level].rho;
     info->omega_p = c->h.levels[level].omega_p;
     return PAMG_OK;
@@ -477,6 +496,7 @@ int pamg_get_index_maps(pamg_ctx* c, int32_t level, int32_t part, int64_t* own_t
                         int32_t* ghost_to_owner) {
   return guard(c, [&] {
     const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
     if (own_to_global) std::memcpy(own_to_global, pl.own_to_global.data(), pl.n_own * sizeof(int64_t));
     if (ghost_to_global) std::memcpy(ghost_to_global, pl.ghost_to_global.data(), pl.n_ghost * sizeof(int64_t));
     if (ghost_to_owner) std::memcpy(ghost_to_owner, pl.ghost_to_owner.data(), pl.n_ghost * sizeof(int32_t));
@@ -487,6 +507,7 @@ int pamg_get_index_maps(pamg_ctx* c, int32_t level, int32_t part, int64_t* own_t
 int pamg_get_block(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int64_t* rowptr, int32_t* col, double* val) {
   return guard(c, [&] {
     const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
     need(which >= 0 && which < 6, "bad block id");
     const LocalCsr& m = pl.blk[which];
     if (rowptr && !m.ptr.empty()) std::memcpy(rowptr, m.ptr.data(), m.ptr.size() * sizeof(int64_t));
@@ -499,6 +520,7 @@ int pamg_get_block(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int6
 int pamg_get_aggregates(pamg_ctx* c, int32_t level, int32_t part, int32_t* agg_local) {
   return guard(c, [&] {
     const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
     need((int64_t)pl.agg_local.size() == pl.n_own && agg_local, "no aggregates on this level");
     std::memcpy(agg_local, pl.agg_local.data(), pl.n_own * sizeof(int32_t));
     return PAMG_OK;
@@ -509,6 +531,7 @@ int pamg_get_halo_plan(pamg_ctx* c, int32_t level, int32_t part, int32_t* recv_p
                        int32_t* send_part, int32_t* send_slot0, int32_t* send_count, int32_t* send_idx) {
   return guard(c, [&] {
     const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
     for (size_t k = 0; k < pl.recv.size(); ++k) {
       if (recv_part) recv_part[k] = pl.recv[k].part;
       if (recv_slot0) recv_slot0[k] = pl.recv[k].slot0;
@@ -536,6 +559,7 @@ int pamg_get_coarse_inverse(pamg_ctx* c, int64_t* n, double* inverse_row_major) 
 int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double* diag_l1) {
   return guard(c, [&] {
     const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
     if (diag) std::memcpy(diag, pl.diag.data(), pl.n_own * sizeof(double));
     if (diag_l1) std::memcpy(diag_l1, pl.diag_l1.data(), pl.n_own * sizeof(double));
     return PAMG_OK;

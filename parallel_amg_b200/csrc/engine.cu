@@ -199,6 +199,8 @@ void merged_block(const Hierarchy& h, int l, int which, LocalCsr& out) {
   for (int p = 0; p < h.nparts; ++p) {
     const PartLevel& pl = h.levels[l].parts[p];
     const PartLevel& pr = h.levels[lr].parts[p];
+    if (!pl.full || !pr.full || !h.levels[lc].parts[p].full)
+      throw std::runtime_error("replicated tail needs every part of its levels: the hierarchy was loaded with a smaller tail_rows");
     const LocalCsr &oo = pl.blk[which], &og = pl.blk[which + 1];
     for (int64_t i = 0; i < pr.n_own; ++i) {
       int64_t cnt = 0;
@@ -387,7 +389,7 @@ ArenaLayout arena_layout(const Hierarchy& h, int part) {
     const PartLevel& pl = lev.parts[part];
     a.ghost.push_back(take(2 * (size_t)pl.n_ghost * sizeof(double)));
     a.flags.push_back(take(pl.recv.size() * sizeof(uint32_t)));
-    a.asm_stage.push_back(take(pl.send_idx.size() * sizeof(double)));
+    a.asm_stage.push_back(take((size_t)pl.n_send_entries() * sizeof(double)));
     a.asm_flags.push_back(take(pl.send.size() * sizeof(uint32_t)));
   }
   a.coarse = take(2 * (size_t)h.levels[tail_level_of(h)].n_global * sizeof(double));
@@ -800,9 +802,9 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   for (int l = 0; l < I.L; ++l)
     for (int p = 0; p < I.nparts; ++p) {
       const PartLevel& pl = h->levels[l].parts[p];
-      if (pl.blk[PAMG_A_OG].nnz() > 0) I.need_halo_A[l] = 1;
-      if (pl.blk[PAMG_R_OG].nnz() > 0) I.need_halo_R[l] = 1;
-      if (pl.blk[PAMG_P_OG].nnz() > 0) I.need_halo_P[l] = 1;
+      if (pl.block_nnz(PAMG_A_OG) > 0) I.need_halo_A[l] = 1;
+      if (pl.block_nnz(PAMG_R_OG) > 0) I.need_halo_R[l] = 1;
+      if (pl.block_nnz(PAMG_P_OG) > 0) I.need_halo_P[l] = 1;
     }
 
   I.tail_level = tail_level_of(*h);
@@ -841,6 +843,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     if (part < 0 || part >= I.nparts || I.local_index[part] >= 0) throw std::runtime_error("bad local part list");
     const int dev = device_ids ? device_ids[i] : 0;
     if (dev < 0 || dev >= ndev) throw std::runtime_error("bad device id");
+    if (!h->levels[0].parts[part].full) throw std::runtime_error("local part was loaded as metadata only");
     I.local_index[part] = (int)I.parts.size();
     I.parts.emplace_back(new PartDev);
     PartDev& pd = *I.parts.back();

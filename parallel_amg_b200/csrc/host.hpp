@@ -38,6 +38,11 @@ struct Neighbor {
 
 struct PartLevel {
   bool present = false;
+  bool full = true;                 // false: loaded as metadata only (another rank drives this part)
+  std::vector<int64_t> nnz_meta;    // [6] block nnz when the blocks themselves were not loaded
+  int64_t n_send_meta = -1;         // send_idx.size() when send_idx was not loaded
+  int64_t block_nnz(int b) const { return full || nnz_meta.empty() ? blk[b].nnz() : nnz_meta[b]; }
+  int64_t n_send_entries() const { return full || n_send_meta < 0 ? (int64_t)send_idx.size() : n_send_meta; }
   int64_t n_own = 0, n_ghost = 0, n_own_coarse = 0, n_ghost_coarse = 0;
   std::vector<int64_t> own_to_global, ghost_to_global;
   std::vector<int32_t> ghost_to_owner;
@@ -84,5 +89,8 @@ void rigid_body_modes(const std::vector<double>& coords, std::vector<double>& B)
 // halo plans from the index maps of all parts of a level (also used for external hierarchies)
 void build_halo_plans(Level& lev, int32_t nparts);
 void finalize_external(Hierarchy& h);
+// binary hand-off of a built hierarchy between the ranks of one node (hierarchy_io.cpp)
+void save_hierarchy(const Hierarchy& h, const std::string& path);
+void load_hierarchy(Hierarchy& h, const std::string& path, int32_t keep_part);
 
 }  // namespace pamg

@@ -38,6 +38,33 @@ def main():
     dist.all_gather_object(digs, sha.hexdigest())
     assert len(set(digs)) == 1, "hierarchies differ between ranks"
 
+    # 1b. rank 0 builds / the others load (the hand-off bench.py uses for N > 1): a rank that only LOADED the
+    #     hierarchy holds exactly the same own part and the same metadata for the parts of the other ranks
+    import tempfile
+    paths = [os.path.join(tempfile.gettempdir(), f"pamg_mp_{os.getpid()}.bin") if rank == 0 else None]
+    dist.broadcast_object_list(paths, src=0)
+    if rank == 0:
+        c.hierarchy_save(paths[0])
+    dist.barrier()
+    cl = L.Context(world)
+    cl.hierarchy_load(paths[0], keep_part=rank)
+    dist.barrier()
+    if rank == 0:
+        os.remove(paths[0])
+    assert cl.num_levels() == c.num_levels()
+    for l in range(c.num_levels()):
+        for b in range(6):
+            if l == c.num_levels() - 1 and b >= L.P_OO:
+                continue
+            assert all(np.array_equal(u, v) for u, v in zip(cl.block(l, rank, b), c.block(l, rank, b)))
+        assert all(np.array_equal(u, v) for u, v in zip(cl.index_maps(l, rank), c.index_maps(l, rank)))
+        pa, pb = cl.halo_plan(l, rank), c.halo_plan(l, rank)
+        assert all(np.array_equal(pa[k], pb[k]) for k in pa)
+        for p in range(world):
+            ia, ib = cl.level_info(l, p), c.level_info(l, p)
+            assert (ia.n_own, ia.n_ghost, list(ia.nnz), ia.n_send) == (ib.n_own, ib.n_ghost, list(ib.nnz), ib.n_send)
+    cl.close()
+
     # 2. distributed mul!/dot on every level with ONLY this rank's part + its halo plan
     A = O.poisson_fd(dims)
     owner = O.uniform_partition(pp, dims)

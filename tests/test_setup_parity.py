@@ -133,6 +133,43 @@ def test_elasticity_gallery_and_nullspace_setup_match_oracle(dims, pp):
     check_structure(c2, h)
 
 
+def test_hierarchy_save_load_roundtrip(tmp_path):
+    """Rank-0-builds / others-load hand-off: a saved hierarchy loads back bit for bit; with keep_part the other
+    parts come back as metadata (sizes, nnz, halo neighbours) except on the small replicated-tail levels."""
+    dims, pp = (20, 20, 20), (2, 2, 1)
+    A, owner, h = oracle_problem(dims, pp)
+    c = L.Context(4)
+    c.gallery_poisson(dims, pp)
+    c.setup(c.default_options(tail_rows=700))
+    path = str(tmp_path / "h.bin")
+    c.hierarchy_save(path)
+    c_all = L.Context(4)
+    c_all.hierarchy_load(path)
+    check_structure(c_all, h)
+    c1 = L.Context(4)
+    c1.hierarchy_load(path, keep_part=1)
+    nl = c1.num_levels()
+    for l in range(nl):
+        small = c1.level_info(l, 0).n_global <= 700 or l == nl - 1
+        for p in range(4):
+            a, b = c1.level_info(l, p), c.level_info(l, p)
+            assert (a.n_own, a.n_ghost, list(a.nnz), a.n_send, a.n_recv_nbrs, a.n_send_nbrs) == \
+                   (b.n_own, b.n_ghost, list(b.nnz), b.n_send, b.n_recv_nbrs, b.n_send_nbrs)
+            if p == 1 or small:
+                assert np.array_equal(c1.index_maps(l, p)[0], c.index_maps(l, p)[0])
+                for blk in range(6):
+                    if l == nl - 1 and blk >= L.P_OO:
+                        continue
+                    assert all(np.array_equal(x, y) for x, y in zip(c1.block(l, p, blk), c.block(l, p, blk)))
+            else:
+                with pytest.raises(L.PamgError):
+                    c1.index_maps(l, p)
+    with pytest.raises(L.PamgError):
+        L.Context(2).hierarchy_load(path)            # written for 4 parts
+    with pytest.raises(L.PamgError):
+        c1.hierarchy_load(str(tmp_path / "missing.bin"))
+
+
 def test_near_nullspace_argument_checks():
     c = L.Context(1)
     c.gallery_poisson((6, 6), (1, 1))
