@@ -22,14 +22,26 @@ CASES = [
     dict(dims=[48, 48, 48], parts=[1, 1, 1], opts={}),
     dict(dims=[24, 24, 24], parts=[2, 2, 1], opts={"smoother": "l1jacobi"}),
     dict(dims=[24, 24, 24], parts=[2, 2, 1], opts={"smoother": "chebyshev", "cheb_degree": 3}),
+    # BASELINE.json configs[3] / configs[4] at fixture size
+    dict(dims=[10, 9, 8], parts=[2, 2, 1], opts={"coarse_size": 60}, kind="elasticity"),
+    dict(dims=[16, 16, 16], parts=[2, 2, 2], opts={"eps_strength": 0.0831}, kind="jump"),
 ]
 
 
-def run_case(dims, parts, opts):
+def run_case(dims, parts, opts, kind="poisson"):
     dims, parts = tuple(dims), tuple(parts)
-    A = O.poisson_fd(dims)
-    owner = O.uniform_partition(parts, dims)
     P = int(np.prod(parts))
+    opts = dict(opts)
+    if kind == "elasticity":
+        A, coords = O.elasticity_q1(dims)
+        owner = np.repeat(O.uniform_partition(parts, dims), 3).astype(np.int32)
+        opts.update(block_size=3, nullspace=O.rigid_body_modes(coords))
+    elif kind == "jump":
+        A = O.diffusion_fv(dims, O.jump_coefficient_k(dims, blocks=4, kmax=1.0e4, eps_z=1.0e-3))
+        owner = O.uniform_partition(parts, dims)
+    else:
+        A = O.poisson_fd(dims)
+        owner = O.uniform_partition(parts, dims)
     h = O.build(A, owner, P, opts)
     gh = h["global"]
     n = A.shape[0]
@@ -54,7 +66,7 @@ def run_case(dims, parts, opts):
 if __name__ == "__main__":
     out = dict(generator="tests/golden/make_golden.py", cases=[])
     for c in CASES:
-        r = run_case(c["dims"], c["parts"], c["opts"])
+        r = run_case(c["dims"], c["parts"], c["opts"], c.get("kind", "poisson"))
         r.update(c)
         out["cases"].append(r)
         print(c, "->", r["level_sizes"], r["iters"])
