@@ -184,6 +184,24 @@ int pamg_get_halo_plan(pamg_ctx* c, int32_t level, int32_t part, int32_t* recv_p
 int pamg_get_coarse_inverse(pamg_ctx* c, int64_t* n, double* inverse_row_major /* may be NULL */);
 int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double* diag_l1);
 
+/* ---- device layouts of one own-own block (which = PAMG_A_OO / PAMG_P_OO / PAMG_R_OO), computed on the host exactly
+ * as the upload does, so that their invariants can be checked without a GPU.  Output arrays may be NULL; call once
+ * with NULL arrays to get the sizes.
+ * SELL-C-sigma: slice sl holds rows perm[sl*C .. sl*C+C); entry j of slot q is at (slice_off[sl] + j) * C + q;
+ *   stored = slice_off[n_slices] * C entries; padding is (0.0, a valid column).
+ * CSR-stream: n_blocks + 1 {first_row, first_entry} pairs (the last one = {nrows, nnz}); n_blocks = -1 when a row
+ *   does not fit max_entries.
+ * boundary rows: rows that also have own-ghost entries, stored whole (own-column entries [ptr[k], mid[k]), ghost-column
+ *   entries [mid[k], ptr[k+1])); skip[row] = 1 marks them (nrows bytes). */
+int pamg_layout_sell(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
+                     int64_t* n_slices, int64_t* stored, int32_t* permuted, int32_t* slice_off, int32_t* col,
+                     double* val, int32_t* perm);
+int pamg_layout_stream(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t max_rows, int32_t max_entries,
+                       int64_t* n_blocks, int32_t* first_row, int32_t* first_entry);
+int pamg_layout_boundary(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int64_t* n_rows, int64_t* n_entries,
+                         int32_t* lanes, int32_t* rows, int32_t* ptr, int32_t* mid, int32_t* col, double* val,
+                         uint8_t* skip);
+
 /* ---- device residency ------------------------------------------------------------------
  * Upload the parts this process drives.  One part per GPU is the production layout; several
  * parts may share one device (PartitionedArrays "debug backend" on one GPU).  With

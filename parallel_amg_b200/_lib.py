@@ -78,6 +78,10 @@ PROTOTYPES = {
                           _P(_i64p), _P(_i32p), _P(_f64p), C.c_double],
     "pamg_coarse_upload": [_ctx, C.c_int64, _f64p],
     "pamg_hierarchy_end": [_ctx],
+    "pamg_layout_sell": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p, _i32p, _i32p, _i32p, _f64p, _i32p],
+    "pamg_layout_stream": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i32p, _i32p],
+    "pamg_layout_boundary": [_ctx, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p, _i32p, _i32p, _i32p, _i32p, _i32p, _f64p,
+                             _P(C.c_uint8)],
     "pamg_hierarchy_save": [_ctx, C.c_char_p],
     "pamg_hierarchy_load": [_ctx, C.c_char_p, C.c_int32],
     "pamg_num_levels": [_ctx, _i32p],
@@ -347,6 +351,43 @@ class Context:
         d, d1 = np.empty(i.n_own), np.empty(i.n_own)
         self._ck(self.lib.pamg_get_diag(self._h, level, part, _ptr(d, C.c_double), _ptr(d1, C.c_double)))
         return d, d1
+
+    # ---- device layouts (host-side conversions, no GPU needed) ----
+    def layout_sell(self, level, part, which, rows_per_slice=64, sigma=1):
+        ns, st, pm = C.c_int64(), C.c_int64(), C.c_int32()
+        self._ck(self.lib.pamg_layout_sell(self._h, level, part, which, rows_per_slice, sigma, C.byref(ns), C.byref(st),
+                                           C.byref(pm), None, None, None, None))
+        i = self.level_info(level, part)
+        nr = i.n_own_coarse if which >= R_OO else i.n_own
+        off, col, val = np.zeros(ns.value + 1, np.int32), np.zeros(st.value, np.int32), np.zeros(st.value)
+        perm = np.zeros(nr, np.int32)
+        self._ck(self.lib.pamg_layout_sell(self._h, level, part, which, rows_per_slice, sigma, C.byref(ns), C.byref(st),
+                                           C.byref(pm), _ptr(off, C.c_int32), _ptr(col, C.c_int32), _ptr(val, C.c_double),
+                                           _ptr(perm, C.c_int32)))
+        return dict(slice_off=off, col=col, val=val, perm=perm, permuted=bool(pm.value), C=rows_per_slice)
+
+    def layout_stream(self, level, part, which, max_rows=1024, max_entries=3069):
+        nb = C.c_int64()
+        self._ck(self.lib.pamg_layout_stream(self._h, level, part, which, max_rows, max_entries, C.byref(nb), None, None))
+        if nb.value < 0:
+            return None
+        r, e = np.zeros(nb.value + 1, np.int32), np.zeros(nb.value + 1, np.int32)
+        self._ck(self.lib.pamg_layout_stream(self._h, level, part, which, max_rows, max_entries, C.byref(nb),
+                                             _ptr(r, C.c_int32), _ptr(e, C.c_int32)))
+        return r, e
+
+    def layout_boundary(self, level, part, which):
+        n, ne, ln = C.c_int64(), C.c_int64(), C.c_int32()
+        self._ck(self.lib.pamg_layout_boundary(self._h, level, part, which, C.byref(n), C.byref(ne), C.byref(ln),
+                                               None, None, None, None, None, None))
+        i = self.level_info(level, part)
+        nr = i.n_own_coarse if which >= R_OO else i.n_own
+        rows, ptr, mid = np.zeros(n.value, np.int32), np.zeros(n.value + 1, np.int32), np.zeros(n.value, np.int32)
+        col, val, skip = np.zeros(ne.value, np.int32), np.zeros(ne.value), np.zeros(max(nr, 1), np.uint8)
+        self._ck(self.lib.pamg_layout_boundary(self._h, level, part, which, C.byref(n), C.byref(ne), C.byref(ln),
+                                               _ptr(rows, C.c_int32), _ptr(ptr, C.c_int32), _ptr(mid, C.c_int32),
+                                               _ptr(col, C.c_int32), _ptr(val, C.c_double), _ptr(skip, C.c_uint8)))
+        return dict(rows=rows, ptr=ptr, mid=mid, col=col, val=val, skip=skip[:nr], lanes=ln.value)
 
     # ---- device ----
     def device_init(self, local_parts=None, device_ids=None):

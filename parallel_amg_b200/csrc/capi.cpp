@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "formats.hpp"
 #include "host.hpp"
 
 using namespace pamg;
@@ -302,6 +303,72 @@ int pamg_setup(pamg_ctx* c, const pamg_options* o) {
     c->eng.reset();
     if (c->ns_k > 0) need((int64_t)c->nullspace.size() == c->A.nrows * c->ns_k, "near-nullspace does not match the matrix");
     build_hierarchy(c->A, c->owner, c->nparts, opt, c->h, c->block_size, c->ns_k, c->ns_k > 0 ? &c->nullspace : nullptr);
+    return PAMG_OK;
+  });
+}
+
+// ---- device-layout queries (host-side conversions of formats.hpp; no GPU needed) ------------------------
+int pamg_layout_sell(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
+                     int64_t* n_slices, int64_t* stored, int32_t* permuted, int32_t* slice_off, int32_t* col, double* val,
+                     int32_t* perm) {
+  return guard(c, [&] {
+    const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
+    need(which == PAMG_A_OO || which == PAMG_P_OO || which == PAMG_R_OO, "SELL applies to own-own blocks");
+    need(rows_per_slice >= 1 && rows_per_slice <= 1024 && n_slices && stored && permuted, "bad arguments");
+    SellHost sh;
+    sell_layout(pl.blk[which], rows_per_slice, sigma, sh, col != nullptr || val != nullptr);
+    const int64_t ns = (int64_t)sh.off.size() - 1;
+    *n_slices = ns;
+    *stored = (int64_t)sh.off[ns] * rows_per_slice;
+    *permuted = sh.permuted ? 1 : 0;
+    if (slice_off) std::memcpy(slice_off, sh.off.data(), sh.off.size() * sizeof(int32_t));
+    if (col) std::memcpy(col, sh.col.data(), (size_t)*stored * sizeof(int32_t));
+    if (val) std::memcpy(val, sh.val.data(), (size_t)*stored * sizeof(double));
+    if (perm) std::memcpy(perm, sh.perm.data(), sh.perm.size() * sizeof(int32_t));
+    return PAMG_OK;
+  });
+}
+
+int pamg_layout_stream(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t max_rows, int32_t max_entries,
+                       int64_t* n_blocks, int32_t* first_row, int32_t* first_entry) {
+  return guard(c, [&] {
+    const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
+    need(which == PAMG_A_OO || which == PAMG_P_OO || which == PAMG_R_OO, "CSR-stream applies to own-own blocks");
+    need(max_rows >= 1 && max_entries >= 1 && n_blocks, "bad arguments");
+    std::vector<std::pair<int32_t, int32_t>> blk;
+    if (!stream_row_blocks(pl.blk[which], max_rows, max_entries, blk)) {
+      *n_blocks = -1;  // a row exceeds the buffer: the block keeps the sub-warp CSR kernel
+      return PAMG_OK;
+    }
+    *n_blocks = (int64_t)blk.size() - 1;
+    for (size_t k = 0; k < blk.size(); ++k) {
+      if (first_row) first_row[k] = blk[k].first;
+      if (first_entry) first_entry[k] = blk[k].second;
+    }
+    return PAMG_OK;
+  });
+}
+
+int pamg_layout_boundary(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int64_t* n_rows, int64_t* n_entries,
+                         int32_t* lanes, int32_t* rows, int32_t* ptr, int32_t* mid, int32_t* col, double* val, uint8_t* skip) {
+  return guard(c, [&] {
+    const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
+    need(which == PAMG_A_OO || which == PAMG_P_OO || which == PAMG_R_OO, "pass the own-own block id");
+    need(n_rows && n_entries && lanes, "bad arguments");
+    BndHost hb;
+    bnd_layout(pl.blk[which], pl.blk[which + 1], hb);
+    *n_rows = (int64_t)hb.rows.size();
+    *n_entries = (int64_t)hb.col.size();
+    *lanes = hb.lanes;
+    if (rows) std::memcpy(rows, hb.rows.data(), hb.rows.size() * sizeof(int32_t));
+    if (ptr) std::memcpy(ptr, hb.ptr.data(), hb.ptr.size() * sizeof(int32_t));
+    if (mid) std::memcpy(mid, hb.mid.data(), hb.mid.size() * sizeof(int32_t));
+    if (col) std::memcpy(col, hb.col.data(), hb.col.size() * sizeof(int32_t));
+    if (val) std::memcpy(val, hb.val.data(), hb.val.size() * sizeof(double));
+    if (skip) std::memcpy(skip, hb.skip.data(), (size_t)pl.blk[which].nrows);
     return PAMG_OK;
   });
 }

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "formats.hpp"
 #include "kernels.cuh"
 
 namespace pamg {
@@ -82,63 +83,6 @@ struct DevCsr {
   SellView slview() const { return SellView{sl_off.p, sl_col.p, sl_val.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
 };
 
-// host-side SELL-C-sigma conversion of one own-own block; returns stored entries / nnz
-struct SellHost {
-  std::vector<int32_t> off, col, perm;
-  std::vector<double> val;
-  bool permuted = false;
-  double fill = 1.0;
-};
-
-void sell_layout(const LocalCsr& m, int C, int sigma, SellHost& out, bool fill_arrays) {
-  const int64_t nr = m.nrows;
-  const int64_t ns = (nr + C - 1) / C;
-  out.perm.resize(nr);
-  for (int64_t i = 0; i < nr; ++i) out.perm[i] = (int32_t)i;
-  out.permuted = false;
-  if (sigma > 1) {
-    for (int64_t w0 = 0; w0 < nr; w0 += sigma) {
-      const int64_t w1 = std::min<int64_t>(nr, w0 + sigma);
-      std::stable_sort(out.perm.begin() + w0, out.perm.begin() + w1, [&](int32_t a, int32_t b) {
-        return (m.ptr[a + 1] - m.ptr[a]) > (m.ptr[b + 1] - m.ptr[b]);
-      });
-    }
-    for (int64_t i = 0; i < nr && !out.permuted; ++i) out.permuted = out.perm[i] != (int32_t)i;
-  }
-  out.off.assign(ns + 1, 0);
-  for (int64_t sl = 0; sl < ns; ++sl) {
-    int64_t w = 0;
-    for (int64_t slot = sl * C; slot < std::min<int64_t>(nr, (sl + 1) * C); ++slot) {
-      const int32_t r = out.perm[slot];
-      w = std::max<int64_t>(w, m.ptr[r + 1] - m.ptr[r]);
-    }
-    const int64_t nxt = (int64_t)out.off[sl] + w;
-    if (nxt * C > INT32_MAX) throw std::runtime_error("SELL storage exceeds int32 entries");
-    out.off[sl + 1] = (int32_t)nxt;
-  }
-  const int64_t stored = (int64_t)out.off[ns] * C;
-  out.fill = m.nnz() ? (double)stored / (double)m.nnz() : 1.0;
-  if (!fill_arrays) return;
-  out.col.assign(stored + 4, 0);
-  out.val.assign(stored + 4, 0.0);
-#pragma omp parallel for schedule(static)
-  for (int64_t sl = 0; sl < ns; ++sl) {
-    const int64_t w = out.off[sl + 1] - out.off[sl];
-    for (int64_t q = 0; q < C; ++q) {
-      const int64_t slot = sl * C + q;
-      if (slot >= nr) continue;  // tail rows of the last slice stay (0.0, column 0)
-      const int32_t r = out.perm[slot];
-      const int64_t b = m.ptr[r], len = m.ptr[r + 1] - b;
-      const int32_t padcol = len ? m.col[b + len - 1] : 0;
-      for (int64_t j = 0; j < w; ++j) {
-        const int64_t dst = ((int64_t)out.off[sl] + j) * C + q;
-        out.col[dst] = j < len ? m.col[b + j] : padcol;
-        out.val[dst] = j < len ? m.val[b + j] : 0.0;
-      }
-    }
-  }
-}
-
 // boundary rows of one operator (rows of the own-own block that also have own-ghost entries), stored
 // whole for the boundary role: own-column entries then ghost-column entries
 struct DevBnd {
@@ -152,37 +96,16 @@ struct DevBnd {
 int pick_lanes(double mean);
 
 void build_bnd(const LocalCsr& oo, const LocalCsr& og, DevBnd& d) {
-  const int64_t nr = oo.nrows;
-  std::vector<int32_t> rows, ptr{0}, mid, col;
-  std::vector<double> val;
-  std::vector<uint8_t> skip((size_t)std::max<int64_t>(nr, 1), 0);
-  if (!og.ptr.empty())
-    for (int64_t i = 0; i < nr; ++i) {
-      if (og.ptr[i + 1] == og.ptr[i]) continue;
-      rows.push_back((int32_t)i);
-      skip[i] = 1;
-      if (!oo.ptr.empty())
-        for (int64_t k = oo.ptr[i]; k < oo.ptr[i + 1]; ++k) {
-          col.push_back(oo.col[k]);
-          val.push_back(oo.val[k]);
-        }
-      mid.push_back((int32_t)col.size());
-      for (int64_t k = og.ptr[i]; k < og.ptr[i + 1]; ++k) {
-        col.push_back(og.col[k]);
-        val.push_back(og.val[k]);
-      }
-      ptr.push_back((int32_t)col.size());
-    }
-  d.n = (int)rows.size();
-  // latency-bound role: one thread per row up to 16 entries (all its loads are independent), wider above
-  const double mean = d.n ? (double)col.size() / d.n : 0.0;
-  d.lanes = mean <= 16 ? 1 : mean <= 32 ? 2 : mean <= 64 ? 4 : mean <= 128 ? 8 : mean <= 256 ? 16 : 32;
-  d.rows.upload(rows);
-  d.ptr.upload(ptr);
-  d.mid.upload(mid);
-  d.col.upload(col);
-  d.val.upload(val);
-  d.skip.upload(skip);
+  BndHost hb;
+  bnd_layout(oo, og, hb);
+  d.n = (int)hb.rows.size();
+  d.lanes = hb.lanes;
+  d.rows.upload(hb.rows);
+  d.ptr.upload(hb.ptr);
+  d.mid.upload(hb.mid);
+  d.col.upload(hb.col);
+  d.val.upload(hb.val);
+  d.skip.upload(hb.skip);
 }
 
 // Rows of all parts of one operator merged into one matrix in gid numbering (replicated coarse tail).
@@ -337,22 +260,11 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
   }
   if (!compress && nr > 0 && fmt != PAMG_FORMAT_CSR) {
     // greedy row blocks: <= S_ROWS rows and <= S_CAP - 3 entries (so the 4-aligned window fits)
+    std::vector<std::pair<int32_t, int32_t>> hb;
+    const bool ok = stream_row_blocks(m, S_ROWS, S_CAP - 3, hb);
     std::vector<int2> blk;
-    int64_t r = 0;
-    bool ok = true;
-    while (r < nr) {
-      const int64_t e0 = m.ptr[r];
-      int64_t r1 = r;
-      while (r1 < nr && r1 - r < S_ROWS && m.ptr[r1 + 1] - e0 <= S_CAP - 3) ++r1;
-      if (r1 == r) {  // a single row exceeds the product buffer: keep the vector kernel for this matrix
-        ok = false;
-        break;
-      }
-      blk.push_back(make_int2((int)r, (int)e0));
-      r = r1;
-    }
+    for (auto& e : hb) blk.push_back(make_int2(e.first, e.second));
     if (ok) {
-      blk.push_back(make_int2((int)nr, (int)m.ptr[nr]));
       d.nblocks = (int)blk.size() - 1;
       d.blk.upload(blk);
       d.stream = true;

@@ -1,0 +1,114 @@
+"""Device layouts (SELL-C-sigma slices, CSR-stream row blocks, boundary-row lists) are built on the host by the
+same code the upload uses (csrc/formats.hpp) and queried through the C ABI, so their invariants are checked here
+without a GPU: every CSR entry appears exactly once in its row's slot, padding is (0.0, valid column), the row
+permutation stays inside its sigma window and sorts by length, row blocks respect the buffer limits, boundary rows
+are exactly the rows with ghost columns, and y = A x computed FROM the layout equals the CSR product bit for bit."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from parallel_amg_b200 import _lib as L
+from util import det_vector
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = L.Context(4)
+    c.gallery_poisson((17, 15, 13), (2, 2, 1))
+    c.setup(c.default_options(coarse_size=40))
+    return c
+
+
+def blocks(c):
+    for l in range(c.num_levels() - 1):
+        for p in range(c.nparts):
+            for which in (L.A_OO, L.P_OO, L.R_OO):
+                yield l, p, which
+
+
+def csr_of(c, l, p, which):
+    ip, ix, d = c.block(l, p, which)
+    i = c.level_info(l, p)
+    ncols = {L.A_OO: i.n_own, L.P_OO: i.n_own_coarse, L.R_OO: i.n_own}[which]
+    return sp.csr_matrix((d, ix, ip), shape=(len(ip) - 1, max(ncols, 1)))
+
+
+@pytest.mark.parametrize("C,sigma", [(32, 1), (64, 1), (64, 256), (32, 96)])
+def test_sell_layout_invariants(ctx, C, sigma):
+    for l, p, which in blocks(ctx):
+        A = csr_of(ctx, l, p, which)
+        nr = A.shape[0]
+        lay = ctx.layout_sell(l, p, which, C, sigma)
+        off, col, val, perm = lay["slice_off"], lay["col"], lay["val"], lay["perm"]
+        lens = np.diff(A.indptr)
+        assert sorted(perm.tolist()) == list(range(nr))                       # a permutation
+        if sigma <= 1:
+            assert not lay["permuted"] and np.array_equal(perm, np.arange(nr))
+        else:
+            for w0 in range(0, nr, sigma):                                     # inside its window, longest rows first
+                w = perm[w0:w0 + sigma]
+                assert w.min() >= w0 and w.max() < w0 + sigma
+                assert np.all(np.diff(lens[w]) <= 0)
+        x = det_vector(A.shape[1], 7)
+        y = np.zeros(nr)
+        for sl in range(len(off) - 1):
+            width = off[sl + 1] - off[sl]
+            for q in range(C):
+                slot = sl * C + q
+                if slot >= nr:
+                    continue
+                r = perm[slot]
+                idx = (off[sl] + np.arange(width)) * C + q
+                cc, vv = col[idx], val[idx]
+                n = lens[r]
+                assert width >= n
+                assert np.array_equal(cc[:n], A.indices[A.indptr[r]:A.indptr[r + 1]])
+                assert np.array_equal(vv[:n], A.data[A.indptr[r]:A.indptr[r + 1]])
+                assert np.all(vv[n:] == 0.0) and np.all((cc[n:] >= 0) & (cc[n:] < A.shape[1]))
+                s = 0.0
+                for k in range(width):                                         # the kernel's order: sequential, product rounded first
+                    s = s + vv[k] * x[cc[k]]
+                y[r] = s
+        ref = np.zeros(nr)
+        for r in range(nr):
+            s = 0.0
+            for k in range(A.indptr[r], A.indptr[r + 1]):
+                s = s + A.data[k] * x[A.indices[k]]
+            ref[r] = s
+        assert np.array_equal(y, ref)
+
+
+def test_stream_row_blocks_respect_limits(ctx):
+    for l, p, which in blocks(ctx):
+        A = csr_of(ctx, l, p, which)
+        for max_rows, max_entries in ((1024, 3069), (256, 500), (7, 64)):
+            out = ctx.layout_stream(l, p, which, max_rows, max_entries)
+            lens = np.diff(A.indptr)
+            if out is None:
+                assert lens.max() > max_entries
+                continue
+            r, e = out
+            assert r[0] == 0 and r[-1] == A.shape[0] and e[-1] == A.nnz
+            assert np.all(np.diff(r) >= 1) and np.all(np.diff(r) <= max_rows)
+            assert np.array_equal(e, A.indptr[r])
+            assert np.all(np.diff(e) <= max_entries)
+            for k in range(len(r) - 2):   # greedy: the next row would not have fitted
+                nxt = r[k + 1]
+                assert (r[k + 1] - r[k] == max_rows) or (A.indptr[nxt + 1] - e[k] > max_entries)
+
+
+def test_boundary_rows_are_the_rows_with_ghost_columns(ctx):
+    for l, p, which in blocks(ctx):
+        oo = csr_of(ctx, l, p, which)
+        ip, ix, d = ctx.block(l, p, which + 1)
+        lay = ctx.layout_boundary(l, p, which)
+        has_ghost = np.diff(ip) > 0
+        assert np.array_equal(lay["rows"], np.flatnonzero(has_ghost))
+        assert np.array_equal(lay["skip"].astype(bool), has_ghost)
+        assert lay["lanes"] in (1, 2, 4, 8, 16, 32)
+        for k, r in enumerate(lay["rows"]):
+            a, m, b = lay["ptr"][k], lay["mid"][k], lay["ptr"][k + 1]
+            assert np.array_equal(lay["col"][a:m], oo.indices[oo.indptr[r]:oo.indptr[r + 1]])
+            assert np.array_equal(lay["val"][a:m], oo.data[oo.indptr[r]:oo.indptr[r + 1]])
+            assert np.array_equal(lay["col"][m:b], ix[ip[r]:ip[r + 1]])
+            assert np.array_equal(lay["val"][m:b], d[ip[r]:ip[r + 1]])
