@@ -1789,7 +1789,8 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
     }
     ++launched;
     if (launched > LOOKAHEAD) {  // status written by k_check number (launched - LOOKAHEAD + 1), straight into pinned memory
-      const uint32_t want = (uint32_t)(launched - LOOKAHEAD + 1);
+      // k_check number 1 is the one of r0, number k + 1 the one of iteration k; none exists beyond maxiter + 1
+      const uint32_t want = (uint32_t)std::min(launched - LOOKAHEAD + 1, maxiter + 1);
       volatile HostStat* hsl = I.hstat + (want % HS_RING);
       const auto t0 = std::chrono::steady_clock::now();
       while (hsl->seq != want) {

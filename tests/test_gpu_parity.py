@@ -293,6 +293,10 @@ def test_pcg_edge_cases():
     n = A.shape[0]
     x, it, hist, ok = c.pcg([np.zeros(n)])                     # zero rhs: 0 iterations, x = 0
     assert ok and it == 0 and np.all(x[0] == 0.0)
+    x, it, hist, ok = c.pcg([det_vector(n, 5)], maxiter=0)     # no iteration allowed: x = 0, only ||r0|| recorded
+    assert (not ok) and it == 0 and len(hist) == 1 and np.all(x[0] == 0.0)
+    x, it, hist, ok = c.pcg([det_vector(n, 5)], maxiter=1)
+    assert (not ok) and it == 1 and len(hist) == 2
     x, it, hist, ok = c.pcg([det_vector(n, 5)], maxiter=3)     # maxiter hit: reported, not raised
     assert (not ok) and it == 3 and len(hist) == 4
     xs, it_ref, _ = O.pcg(h, O.pvector_from_global(lev, det_vector(n, 5)), precond=False, maxiter=500)
