@@ -1,11 +1,12 @@
 // engine.cu — device-resident hierarchy, halo/all-reduce wiring over peer memory, V-cycle and
 // PCG schedules (CUDA graphs), behind the C ABI of include/pamg.h.
 //
-// Layout in HBM, per (level, part): split CSR blocks A_oo / A_og, P_oo / P_og, R_oo / R_og
-// (fp64 values, int32 local columns, int32 row pointers; own-ghost blocks stored as a compressed
-// list of boundary rows), smoother weights, and own-length work vectors.  Ghost values never
-// live in the vectors: they arrive in a per-level, double-buffered staging area inside the
-// part's peer-visible "arena", written directly by the neighbouring GPUs.
+// Layout in HBM, per (level, part): the own-own blocks of A, P, R in SELL-C-sigma, CSR-stream or plain CSR
+// (fp64 values, int32 local columns; formats.hpp), the rows that also have own-ghost entries once more as
+// whole "boundary rows", smoother weights, and own-length work vectors.  Ghost values never live in the
+// vectors: they arrive in a per-level, double-buffered staging area inside the part's peer-visible
+// "arena", written directly by the neighbouring GPUs.  Levels below the tail threshold exist a second
+// time, merged over all parts, on every GPU (replicated coarse tail).
 #include <algorithm>
 #include <chrono>
 #include <cmath>

@@ -72,7 +72,7 @@ struct DevState {
   int32_t error;
   int32_t maxiter;
   double sc[SC_COUNT];
-  double dot_main;  // partial of the main (own-own) kernel, completed by the own-ghost kernel
+  double dot_main;  // split launches: partial of the main launch, completed and published by k_boundary
   uint32_t check_seq;  // k_check executions since k_pcg_init
   unsigned long long* trace;  // != nullptr: CTA 0 of every kernel appends its start time (globaltimer, ns)
   uint32_t trace_pos, trace_cap;
@@ -253,7 +253,7 @@ __device__ __forceinline__ void red_consume(DevState* st, const RedCtx& rc, doub
 }
 
 // block-level finish of a fused dot: per-block partials -> last block sums them in block order.
-// publish: 0 = store the local total in st->dot_main (an own-ghost kernel follows and publishes),
+// publish: 0 = store the local total in st->dot_main (a k_boundary launch follows and publishes),
 //          1 = publish total (+ st->dot_main if add_main) to all parts.
 __device__ __forceinline__ void dot_finish(double acc, double* partials, DevState* st, uint32_t* ticket,
                                            const RedCtx& rc, int publish, int add_main, int slot) {
