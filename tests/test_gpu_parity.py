@@ -304,6 +304,24 @@ def test_pcg_edge_cases():
     assert ok and it == it_ref
 
 
+def test_part_without_rows_on_device():
+    """A part that owns nothing takes part in every exchange and all-reduce with empty arrays."""
+    A = O.poisson_fd((12, 12, 12))
+    n = A.shape[0]
+    owner = np.zeros(n, np.int32)
+    owner[n // 2:] = 2
+    h = O.build(A, owner, 3)
+    c = product_context_from_oracle(h)
+    c.device_init()
+    lev = h["levels"][0]
+    b = det_vector(n, 13)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, b))
+    x, it, hist, ok = c.pcg(own_parts(lev, b))
+    assert ok and it == it_ref and len(x[1]) == 0
+
+
 def test_single_level_hierarchy_is_a_direct_solve():
     A, h, c = make((7, 5), (1, 1))
     b = det_vector(35, 7)

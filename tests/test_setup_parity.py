@@ -133,6 +133,21 @@ def test_elasticity_gallery_and_nullspace_setup_match_oracle(dims, pp):
     check_structure(c2, h)
 
 
+def test_part_without_rows():
+    """An index partition may leave a part empty (PartitionedArrays allows it): the setup keeps it as a part with
+    zero own rows on every level, exactly like the oracle."""
+    A = O.poisson_fd((12, 12, 12))
+    n = A.shape[0]
+    owner = np.zeros(n, np.int32)
+    owner[n // 2:] = 2                      # part 1 owns nothing
+    h = O.build(A, owner, 3)
+    c = L.Context(3)
+    c.set_matrix_global(A.indptr, A.indices, A.data, owner)
+    c.setup()
+    check_structure(c, h)
+    assert all(c.level_info(l, 1).n_own == 0 for l in range(c.num_levels()))
+
+
 def test_hierarchy_save_load_roundtrip(tmp_path):
     """Rank-0-builds / others-load hand-off: a saved hierarchy loads back bit for bit; with keep_part the other
     parts come back as metadata (sizes, nnz, halo neighbours) except on the small replicated-tail levels."""
