@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -856,8 +858,22 @@ static void fill_diag(PartLevel& pl) {
 // ------------------------------------------------------------------------------------------
 // whole setup
 // ------------------------------------------------------------------------------------------
+namespace {
+struct PhaseTimer {  // PAMG_SETUP_TIMING=1: per-phase wall time of the host setup on stderr
+  bool on = std::getenv("PAMG_SETUP_TIMING") != nullptr;
+  double t0 = omp_get_wtime();
+  void lap(const char* what, int level) {
+    if (!on) return;
+    const double t1 = omp_get_wtime();
+    std::fprintf(stderr, "[pamg setup] level %d %-22s %8.3f s\n", level, what, t1 - t0);
+    t0 = t1;
+  }
+};
+}  // namespace
+
 void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t nparts, const pamg_options& o, Hierarchy& h,
                      int32_t block_size, int32_t ns_k, const std::vector<double>* nullspace) {
+  PhaseTimer tm;
   if (A0.nrows != (int64_t)owner0.size()) throw std::runtime_error("owner size mismatch");
   const bool use_ns = nullspace && ns_k > 0;
   if (block_size < 1) block_size = 1;
@@ -894,6 +910,7 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       absdiag[i] = std::fabs(d[i]);
     }
     cur.rho = gershgorin_rho(cur.A, dinv);
+    tm.lap("own index + diagonal", (int)g.size() - 1);
     if (n <= o.coarse_size || (int32_t)g.size() >= o.max_levels) break;
 
     std::vector<std::vector<int32_t>> aggs(nparts);
@@ -956,13 +973,18 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       }
       tentative_from_nullspace(Bcur, kdof, bs, agg_node, nagg, P0, Bc, dead);
     }
+    tm.lap("aggregation + P0", (int)g.size() - 1);
     build_prolongator(cur.A, P0, nc, eps, absdiag, cur.P, &cur.omega_p);
+    tm.lap("prolongator smoothing", (int)g.size() - 1);
     transpose(cur.P, cur.R);
+    tm.lap("transpose", (int)g.size() - 1);
     G nxt;
     {
       Csr AP;
       spgemm(cur.A, cur.P, AP);
+      tm.lap("A*P", (int)g.size() - 1);
       spgemm(cur.R, AP, nxt.A);
+      tm.lap("R*(AP)", (int)g.size() - 1);
     }
     for (int64_t gd : dead) {  // empty coarse column: unit diagonal keeps the Galerkin matrix regular
       bool found = false;
@@ -984,6 +1006,7 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
   }
 
   const int32_t L = (int32_t)g.size();
+  tm.lap("(levels done)", L - 1);
   h.levels.resize(L);
   std::vector<std::vector<GhostLookup>> gl(L, std::vector<GhostLookup>(nparts));
   for (int32_t l = 0; l < L; ++l) {
@@ -1020,8 +1043,10 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     }
     build_halo_plans(lev, nparts);
   }
+  tm.lap("localisation", L - 1);
   h.n_coarse = g[L - 1].A.nrows;
   dense_inverse(g[L - 1].A, h.coarse_inv);
+  tm.lap("dense inverse", L - 1);
   h.coarse_part_offset.assign(nparts + 1, 0);
   for (int32_t p = 0; p < nparts; ++p)
     h.coarse_part_offset[p + 1] = h.coarse_part_offset[p] + h.levels[L - 1].parts[p].n_own;
