@@ -258,6 +258,39 @@ void matvec(const Csr& A, const double* x, double* y) {
 // ------------------------------------------------------------------------------------------
 // structural sparse kernels (explicit zeros are never dropped)
 // ------------------------------------------------------------------------------------------
+// Row accumulator for the structural products: products are added per column in ENCOUNTER order (the order a
+// stable sort by column followed by a sequential sum would use, i.e. the oracle's), then the distinct columns of
+// the row are emitted in ascending order.  slot[] maps a column to its position in the row-local arrays.
+struct RowAccumulator {
+  std::vector<int32_t> slot;
+  std::vector<int64_t> cols;
+  std::vector<double> vals;
+  std::vector<int32_t> order;
+  explicit RowAccumulator(int64_t ncols) : slot((size_t)ncols, -1) {}
+  void clear() {
+    for (int64_t c : cols) slot[c] = -1;
+    cols.clear();
+    vals.clear();
+  }
+  void add(int64_t c, double v) {
+    const int32_t q = slot[c];
+    if (q < 0) {
+      slot[c] = (int32_t)cols.size();
+      cols.push_back(c);
+      vals.push_back(v);
+    } else {
+      vals[q] += v;
+    }
+  }
+  // positions of the row's columns in ascending column order
+  const std::vector<int32_t>& sorted() {
+    order.resize(cols.size());
+    for (size_t q = 0; q < cols.size(); ++q) order[q] = (int32_t)q;
+    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cols[x] < cols[y]; });
+    return order;
+  }
+};
+
 static void spgemm(const Csr& A, const Csr& B, Csr& C) {
   const int64_t n = A.nrows;
   C.nrows = n;
@@ -266,12 +299,11 @@ static void spgemm(const Csr& A, const Csr& B, Csr& C) {
   const int nt = omp_get_max_threads();
   std::vector<std::vector<int64_t>> tcol(nt);
   std::vector<std::vector<double>> tval(nt);
-  std::vector<int64_t> tbeg(nt + 1, 0);
 #pragma omp parallel num_threads(nt)
   {
     const int t = omp_get_thread_num();
     const int64_t r0 = n * t / nt, r1 = n * (t + 1) / nt;
-    std::vector<std::pair<int64_t, double>> acc;
+    RowAccumulator acc(B.ncols);
     auto& oc = tcol[t];
     auto& ov = tval[t];
     for (int64_t i = r0; i < r1; ++i) {
@@ -279,22 +311,13 @@ static void spgemm(const Csr& A, const Csr& B, Csr& C) {
       for (int64_t ka = A.ptr[i]; ka < A.ptr[i + 1]; ++ka) {
         const int64_t k = A.col[ka];
         const double a = A.val[ka];
-        for (int64_t kb = B.ptr[k]; kb < B.ptr[k + 1]; ++kb) acc.emplace_back(B.col[kb], a * B.val[kb]);
+        for (int64_t kb = B.ptr[k]; kb < B.ptr[k + 1]; ++kb) acc.add(B.col[kb], a * B.val[kb]);
       }
-      std::stable_sort(acc.begin(), acc.end(),
-                       [](const std::pair<int64_t, double>& x, const std::pair<int64_t, double>& y) { return x.first < y.first; });
-      int64_t cnt = 0;
-      for (size_t q = 0; q < acc.size();) {
-        int64_t cidx = acc[q].first;
-        double s = acc[q].second;
-        size_t e = q + 1;
-        while (e < acc.size() && acc[e].first == cidx) s += acc[e++].second;
-        oc.push_back(cidx);
-        ov.push_back(s);
-        ++cnt;
-        q = e;
+      for (int32_t q : acc.sorted()) {
+        oc.push_back(acc.cols[q]);
+        ov.push_back(acc.vals[q]);
       }
-      C.ptr[i + 1] = cnt;
+      C.ptr[i + 1] = (int64_t)acc.cols.size();
     }
   }
   for (int64_t i = 0; i < n; ++i) C.ptr[i + 1] += C.ptr[i];
@@ -497,25 +520,21 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
   {
     const int t = omp_get_thread_num();
     const int64_t r0 = n * t / nt, r1 = n * (t + 1) / nt;
-    std::vector<std::pair<int64_t, double>> acc;
+    RowAccumulator acc(nc);
     for (int64_t i = r0; i < r1; ++i) {
       acc.clear();
       for (int64_t k = F->ptr[i]; k < F->ptr[i + 1]; ++k) {
         const int64_t j = F->col[k];
         const double f = F->val[k];
-        for (int64_t kb = P0.ptr[j]; kb < P0.ptr[j + 1]; ++kb) acc.emplace_back(P0.col[kb], f * P0.val[kb]);
+        for (int64_t kb = P0.ptr[j]; kb < P0.ptr[j + 1]; ++kb) acc.add(P0.col[kb], f * P0.val[kb]);
       }
-      std::stable_sort(acc.begin(), acc.end(),
-                       [](const std::pair<int64_t, double>& x, const std::pair<int64_t, double>& y) { return x.first < y.first; });
       const double w = -(omega * dinv[i]);
       int64_t pk = P0.ptr[i];  // next tentative entry of this row still to be placed
       const int64_t pe = P0.ptr[i + 1];
       int64_t cnt = 0;
-      for (size_t q = 0; q < acc.size();) {
-        const int64_t c = acc[q].first;
-        double s = acc[q].second;
-        size_t e = q + 1;
-        while (e < acc.size() && acc[e].first == c) s += acc[e++].second;
+      for (int32_t q : acc.sorted()) {
+        const int64_t c = acc.cols[q];
+        const double s = acc.vals[q];
         while (pk < pe && P0.col[pk] < c) {  // tentative entries without an A_F P0 partner
           tcol[t].push_back(P0.col[pk]);
           tval[t].push_back(P0.val[pk]);
@@ -530,7 +549,6 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
         tcol[t].push_back(c);
         tval[t].push_back(v);
         ++cnt;
-        q = e;
       }
       while (pk < pe) {
         tcol[t].push_back(P0.col[pk]);
