@@ -269,30 +269,14 @@ def main():
     t0 = time.perf_counter()
     opts_kw = wl.get("opts", {})
     if share:
-        import shutil
+        from parallel_amg_b200.distributed import shared_setup
         need_bytes = 400 * int(np.prod(dims)) * (12 if wl.get("kind") == "elasticity" else 1)   # generous file-size estimate
-        shm = "/tmp"
-        for cand in ("/dev/shm", "/tmp"):
-            try:
-                if shutil.disk_usage(cand).free > need_bytes:
-                    shm = cand
-                    break
-            except OSError:
-                pass
-        path = os.path.join(shm, f"pamg_hier_{os.environ.get('MASTER_PORT', '0')}_{args.workload}_{world}.bin")
-        meta = [None]
-        if rank == 0:
-            make_problem(c, wl, nparts)
-            c.setup(c.default_options(**opts_kw))
-            c.hierarchy_save(path)
-            meta = [c.global_size()]
-        dist.broadcast_object_list(meta, src=0)
-        n, nnz = meta[0]
-        if rank != 0:
-            c.hierarchy_load(path, keep_part=rank)
-        dist.barrier()
-        if rank == 0:
-            os.remove(path)
+
+        def build(ctx):
+            make_problem(ctx, wl, nparts)
+            ctx.setup(ctx.default_options(**opts_kw))
+
+        n, nnz = shared_setup(c, build, rank, world, tag=args.workload, need_bytes=need_bytes)
     else:
         make_problem(c, wl, nparts)
         if world > 1:  # replicated setup in waves so that the box's memory holds the concurrent copies
@@ -311,13 +295,8 @@ def main():
         n, nnz = c.global_size()
     setup_s = time.perf_counter() - t0
     if world > 1:
-        c.device_init([rank], [local_rank])
-        blobs = [None] * world
-        dist.all_gather_object(blobs, c.comm_export(rank))
-        for p, bl in enumerate(blobs):
-            if p != rank:
-                c.comm_import(p, bl)
-        c.comm_connect()
+        from parallel_amg_b200.distributed import connect_parts
+        connect_parts(c, rank, world, local_rank)
         mine = [rank]
     else:
         c.device_init([0], [local_rank])

@@ -40,17 +40,15 @@ def main():
 
     # 1b. rank 0 builds / the others load (the hand-off bench.py uses for N > 1): a rank that only LOADED the
     #     hierarchy holds exactly the same own part and the same metadata for the parts of the other ranks
-    import tempfile
-    paths = [os.path.join(tempfile.gettempdir(), f"pamg_mp_{os.getpid()}.bin") if rank == 0 else None]
-    dist.broadcast_object_list(paths, src=0)
-    if rank == 0:
-        c.hierarchy_save(paths[0])
-    dist.barrier()
+    from parallel_amg_b200.distributed import shared_setup
+
+    def build(ctx):
+        ctx.gallery_poisson(dims, pp)
+        ctx.setup()
+
     cl = L.Context(world)
-    cl.hierarchy_load(paths[0], keep_part=rank)
-    dist.barrier()
-    if rank == 0:
-        os.remove(paths[0])
+    n_nnz = shared_setup(cl, build, rank, world, tag="mpcpu")
+    assert tuple(n_nnz) == tuple(c.global_size())
     assert cl.num_levels() == c.num_levels()
     for l in range(c.num_levels()):
         for b in range(6):
