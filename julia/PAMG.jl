@@ -51,7 +51,9 @@ function part_rows(Aloc::SparseMatrixCSC, rows, cols)
     (o2g, rowptr, colgid, Float64.(At.nzval[1:rowptr[end]]))
 end
 
-function setup(A::PSparseMatrix; devices = nothing, opts::Options = default_options())
+# nullspace: optional n x k matrix (global row order) of near-nullspace vectors, e.g. the 6 rigid-body modes from
+# `nullspace_linear_elasticity`; block_size: DOFs per node (3 for 3-D elasticity).
+function setup(A::PSparseMatrix; devices = nothing, opts::Options = default_options(), nullspace = nothing, block_size = 1)
     rows, cols = partition(axes(A, 1)), partition(axes(A, 2))
     np = length(rows)
     r = Ref{Ptr{Cvoid}}(C_NULL)
@@ -67,6 +69,11 @@ function setup(A::PSparseMatrix; devices = nothing, opts::Options = default_opti
         check(ctx, ccall((:pamg_set_part_rows, lib), Cint,
                          (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                          ctx, p - 1, length(o2g), o2g, rowptr, colgid, val))
+    end
+    if nullspace !== nothing
+        B = permutedims(Matrix{Float64}(nullspace))           # row-major n x k for the C side
+        check(ctx, ccall((:pamg_set_near_nullspace, lib), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}),
+                         ctx, block_size, size(nullspace, 2), B))
     end
     check(ctx, ccall((:pamg_setup, lib), Cint, (Ptr{Cvoid}, Ref{Options}), ctx, Ref(opts)))
     local_parts = Int32.(0:np-1)
