@@ -740,8 +740,8 @@ __global__ void __launch_bounds__(BLOCK, RPT == 1 ? 4 : 3) k_spmv_sell(SellView 
       if (slot < A.nrows) {
         const int r = A.perm ? A.perm[slot] : slot;
         if (fh.skip && fh.skip[r]) continue;
-        const double res = apply_epilogue<MODE, DOT>(a, r, s[k]);
-        if (DOT) contrib += res;
+        const double res = apply_epilogue<MODE, false>(a, r, s[k]);
+        if (DOT) contrib += a.dotv[r] * res;  // after the stores: an L1 hit (prefetched above), and it keeps ptxas batching the loop loads
       }
     }
     if (DOT) s_acc[threadIdx.x] += contrib;  // in shared memory: a register live across the entry loop costs its load batching
