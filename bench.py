@@ -414,10 +414,10 @@ def main():
                      ms_per_step=e2e_ms / args.steps),
             gpu_launches=int(launches), clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
-            times, it_cpu, _ = cpu_solve_timed(c, nparts, [b[own[0]]], 2)
+            times, it_cpu, _ = cpu_solve_timed(c, nparts, [b[own[0]]], 4)
             cores = os.cpu_count()
             line["cpu_baseline"] = dict(value=n / min(times), unit="DOF/s", cores=cores, kind="port",
-                                        sample=f"2 whole solves ({it_cpu} iterations each) of the same workload, best of 2; "
+                                        sample=f"4 whole solves ({it_cpu} iterations each) of the same workload, best of 4; "
                                                "C/OpenMP oracle port (no reference code exists)",
                                         seconds=[round(t, 3) for t in times], iters=int(it_cpu))
         else:
