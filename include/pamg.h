@@ -39,6 +39,7 @@ typedef enum {
 } pamg_status;
 
 enum { PAMG_SMOOTHER_JACOBI = 0, PAMG_SMOOTHER_L1JACOBI = 1, PAMG_SMOOTHER_CHEBYSHEV = 2 };
+enum { PAMG_CYCLE_V = 0, PAMG_CYCLE_W = 1 };
 /* kernel family for the own-own blocks: CSR = sub-warp "vector per row" (1..32 lanes chosen from the
  * mean nnz/row; 32 = warp per row); STREAM = CSR-stream (block-cooperative 128-bit coalesced loads of
  * the contiguous val/col ranges, products staged in shared memory); the storage is plain CSR for both.
@@ -72,6 +73,7 @@ typedef struct {
   int32_t sell_rows_per_thread; /* 1 or 2 (C = 32 or 64; 2 => 128-bit value loads); 0: auto */
   int32_t fuse_halo;      /* 1: halo pack / wait / boundary rows run inside the consuming kernel whenever every local
                              part has a GPU of its own; 0: always three launches (env PAMG_FUSE_HALO overrides) */
+  int32_t cycle;          /* PAMG_CYCLE_V (0) or PAMG_CYCLE_W (1): amg_level_params(; cycle = v_cycle | w_cycle) */
 } pamg_options;
 
 typedef struct {

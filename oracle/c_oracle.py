@@ -113,6 +113,30 @@ class COracle:
             levels.append(parts)
         return cls(levels, h["coarse_inv"], h["opts"]["nu_pre"], h["opts"]["nu_post"])
 
+    @classmethod
+    def from_product_context(cls, ctx, nparts, nu_pre=1, nu_post=1, omega=2.0 / 3.0, smoother="jacobi"):
+        """The hierarchy the PRODUCT's host setup built, copied out through the C ABI queries (pamg_get_index_maps /
+        pamg_get_block / pamg_get_diag / pamg_get_coarse_inverse), so that the oracle and the device run the same
+        operators at sizes where the numpy oracle's own setup would take minutes.  ctx: parallel_amg_b200._lib.Context."""
+        from types import SimpleNamespace
+        nl = ctx.num_levels()
+        levels = []
+        for l in range(nl):
+            parts = []
+            for p in range(nparts):
+                own, gh, gho = ctx.index_maps(l, p)
+                d = dict(own_to_global=own, ghost_to_global=gh, ghost_to_owner=gho)
+                for b, name in enumerate(cls.NAMES):
+                    if l == nl - 1 and b >= 2:
+                        continue
+                    ip, ix, dd = ctx.block(l, p, b)
+                    d[name] = SimpleNamespace(indptr=ip, indices=ix, data=dd)
+                dg, dl1 = ctx.diag(l, p)
+                d["w"] = (1.0 / dl1) if smoother == "l1jacobi" else omega / dg
+                parts.append(d)
+            levels.append(parts)
+        return cls(levels, ctx.coarse_inverse(), nu_pre, nu_post)
+
     def _vecs(self, arrs):
         out = (_f64p * self.nparts)()
         keep = [np.ascontiguousarray(a, np.float64) for a in arrs]

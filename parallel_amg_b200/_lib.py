@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libpamg.so")
 OK, ERR_ARG, ERR_CUDA, ERR_NOGPU, ERR_COMM, ERR_NOTCONV, ERR_ALLOC = 0, -1, -2, -3, -4, -5, -6
 SMOOTHER_JACOBI, SMOOTHER_L1JACOBI, SMOOTHER_CHEBYSHEV = 0, 1, 2
 FORMAT_AUTO, FORMAT_CSR, FORMAT_STREAM, FORMAT_SELL = 0, 1, 2, 3
+CYCLE_V, CYCLE_W = 0, 1
 A_OO, A_OG, P_OO, P_OG, R_OO, R_OG = range(6)
 BLOCK_NAMES = ("A_oo", "A_og", "P_oo", "P_og", "R_oo", "R_og")
 
@@ -30,6 +31,7 @@ class Options(C.Structure):
         ("nu_pre", C.c_int32), ("nu_post", C.c_int32), ("cheb_degree", C.c_int32),
         ("cheb_lo_frac", C.c_double), ("cheb_hi_frac", C.c_double), ("spmv_format", C.c_int32),
         ("use_graph", C.c_int32), ("lanes_per_row", C.c_int32), ("tail_rows", C.c_int32), ("sell_sigma", C.c_int32), ("sell_rows_per_thread", C.c_int32), ("fuse_halo", C.c_int32),
+        ("cycle", C.c_int32),
     ]
 
 

@@ -152,6 +152,7 @@ void pamg_default_options(pamg_options* o) {
   o->sell_sigma = 0;
   o->sell_rows_per_thread = 0;
   o->fuse_halo = 1;
+  o->cycle = PAMG_CYCLE_V;
 }
 
 int pamg_create(int32_t nparts, pamg_ctx** out) {
@@ -180,9 +181,10 @@ int pamg_set_part_rows(pamg_ctx* c, int32_t part, int64_t n_own, const int64_t* 
     auto& s = c->staged[part];
     s.own_to_global.assign(own_to_global, own_to_global + n_own);
     if (n_own) {
-      s.rowptr.assign(rowptr, rowptr + n_own + 1);
-      const int64_t nnz = rowptr[n_own] - rowptr[0];
       need(rowptr[0] == 0, "rowptr must start at 0");
+      for (int64_t i = 0; i < n_own; ++i) need(rowptr[i + 1] >= rowptr[i], "rowptr must be non-decreasing");
+      s.rowptr.assign(rowptr, rowptr + n_own + 1);
+      const int64_t nnz = rowptr[n_own];
       need(nnz == 0 || (col_gid && val), "null arrays");
       s.col.assign(col_gid, col_gid + nnz);
       s.val.assign(val, val + nnz);
@@ -206,6 +208,7 @@ int pamg_set_matrix_global(pamg_ctx* c, int64_t n, const int64_t* rowptr, const 
   return guard(c, [&] {
     need(n > 0 && rowptr && col && val && owner, "null arrays");
     need(rowptr[0] == 0, "rowptr must start at 0");
+    for (int64_t i = 0; i < n; ++i) need(rowptr[i + 1] >= rowptr[i], "rowptr must be non-decreasing");
     Csr& A = c->A;
     A.nrows = A.ncols = n;
     A.ptr.assign(rowptr, rowptr + n + 1);
@@ -259,6 +262,8 @@ int pamg_gallery_diffusion_jump(pamg_ctx* c, int32_t ndim, const int64_t* nodes_
 
 int pamg_uniform_partition(int32_t ndim, const int64_t* nodes_per_dir, const int32_t* parts_per_dir, int32_t* owner_out) {
   if (ndim < 1 || ndim > 3 || !nodes_per_dir || !parts_per_dir || !owner_out) return PAMG_ERR_ARG;
+  for (int a = 0; a < ndim; ++a)
+    if (nodes_per_dir[a] < 1 || parts_per_dir[a] < 1 || parts_per_dir[a] > nodes_per_dir[a]) return PAMG_ERR_ARG;
   try {
     std::vector<int32_t> o;
     uniform_partition(ndim, nodes_per_dir, parts_per_dir, o);
@@ -300,6 +305,7 @@ int pamg_setup(pamg_ctx* c, const pamg_options* o) {
     need(opt.coarse_size >= 1 && opt.max_levels >= 1 && opt.max_levels <= 16, "bad coarse_size/max_levels");
     need(opt.nu_pre >= 0 && opt.nu_post >= 0 && opt.nu_pre + opt.nu_post >= 0, "bad sweep counts");
     need(opt.smoother >= 0 && opt.smoother <= 2, "bad smoother");
+    need(opt.cycle == PAMG_CYCLE_V || opt.cycle == PAMG_CYCLE_W, "bad cycle");
     c->eng.reset();
     if (c->ns_k > 0) need((int64_t)c->nullspace.size() == c->A.nrows * c->ns_k, "near-nullspace does not match the matrix");
     build_hierarchy(c->A, c->owner, c->nparts, opt, c->h, c->block_size, c->ns_k, c->ns_k > 0 ? &c->nullspace : nullptr);

@@ -302,7 +302,7 @@ ArenaLayout arena_layout(const Hierarchy& h, int part) {
     const PartLevel& pl = lev.parts[part];
     a.ghost.push_back(take(2 * (size_t)pl.n_ghost * sizeof(double)));
     a.flags.push_back(take(pl.recv.size() * sizeof(uint32_t)));
-    a.asm_stage.push_back(take((size_t)pl.n_send_entries() * sizeof(double)));
+    a.asm_stage.push_back(take(2 * (size_t)pl.n_send_entries() * sizeof(double)));
     a.asm_flags.push_back(take(pl.send.size() * sizeof(uint32_t)));
   }
   a.coarse = take(2 * (size_t)h.levels[tail_level_of(h)].n_global * sizeof(double));
@@ -776,6 +776,11 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     CK(cudaMemset(pd.arena, 0, pd.lay.total));
     I.arena_of[part] = pd.arena;
     pd.st.alloc(1);
+    {
+      unsigned long long tmo = SPIN_TIMEOUT_NS;
+      if (const char* te = getenv("PAMG_SPIN_TIMEOUT_MS")) tmo = std::max(1ll, atoll(te)) * 1000000ull;
+      CK(cudaMemcpy(&pd.st.p->spin_timeout_ns, &tmo, sizeof(tmo), cudaMemcpyHostToDevice));
+    }
     pd.scratch4.alloc(RED_W);
     int max_blocks = Impl::MAX_GRID;
 
@@ -896,12 +901,25 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     for (auto& up : I.parts) per_dev[up->device]++;
     bool alone = true;
     for (auto& kv : per_dev) alone = alone && kv.second == 1;
-    bool symmetric = true;  // every part both sends to and receives from its neighbours on every level
-    for (int l = 0; l < I.L; ++l)
-      for (int p = 0; p < I.nparts; ++p) {
+    // The double-buffered staging is race-free only if a part can never run two exchanges ahead of a part that
+    // still reads its values, i.e. if on every level every part RECEIVES from exactly the parts it SENDS to
+    // (DESIGN.md "Halo protocol").  Structurally symmetric operators give that; an externally uploaded or
+    // non-symmetric hierarchy may not.  One stream for all parts (single-device debug layout) is ordered anyway.
+    bool symmetric = true;
+    for (int l = 0; l < I.L && symmetric; ++l)
+      for (int p = 0; p < I.nparts && symmetric; ++p) {
         const PartLevel& pl = h->levels[l].parts[p];
-        if (pl.recv.empty() != pl.send.empty()) symmetric = false;
+        std::vector<int32_t> rs, ss;
+        for (const Neighbor& nb : pl.recv) rs.push_back(nb.part);
+        for (const Neighbor& nb : pl.send) ss.push_back(nb.part);
+        std::sort(rs.begin(), rs.end());
+        std::sort(ss.begin(), ss.end());
+        if (rs != ss) symmetric = false;
       }
+    const bool one_stream = per_dev.size() == 1 && nlocal == I.nparts;
+    if (!symmetric && !one_stream)
+      throw CommError("halo plan: a part's send-neighbour set differs from its receive-neighbour set (structurally non-symmetric "
+                      "operator); the peer-memory exchange protocol needs symmetric neighbour sets on multi-GPU layouts");
     if (const char* pe = getenv("PAMG_PERSISTENT")) I.persistent = atoi(pe) != 0;
     if (const char* be = getenv("PAMG_BND_FIRST")) I.bnd_first = atoi(be) != 0 ? 1 : 0;
     const char* env = getenv("PAMG_FUSE_HALO");
@@ -1017,7 +1035,8 @@ void Engine::connect() {
         if (idx < 0) throw std::runtime_error("halo plan asymmetry");
         char* qa = I.arena_of[rb.part];
         AsmSendNbr a;
-        a.stage = (double*)(qa + lay[rb.part].asm_stage[l]) + ql.send[idx].offset;
+        a.stage[0] = (double*)(qa + lay[rb.part].asm_stage[l]) + ql.send[idx].offset;
+        a.stage[1] = a.stage[0] + ql.n_send_entries();
         a.flag = (uint32_t*)(qa + lay[rb.part].asm_flags[l]) + idx;
         a.slot0 = rb.slot0;
         a.count = rb.count;
@@ -1644,7 +1663,8 @@ void Engine::assemble(int level, double* const* v) {
     I.set_dev(pd);
     if (ld.n_send_nbrs > 0) {
       k_asm_add<<<I.grid_for(std::max(ld.asm_nrows, 1), BLOCK), BLOCK, 0, pd.stream>>>(
-          pd.io_local.p, ld.asm_rows.p, ld.asm_ptr.p, ld.asm_src.p, ld.asm_nrows, ld.asm_stage, ld.asm_flags, ld.n_send_nbrs,
+          pd.io_local.p, ld.asm_rows.p, ld.asm_ptr.p, ld.asm_src.p, ld.asm_nrows, ld.asm_stage, ld.asm_stage + ld.n_send, ld.asm_flags,
+          ld.n_send_nbrs,
           pd.st.p, level);
       I.note_launch("k_asm_add");
     }

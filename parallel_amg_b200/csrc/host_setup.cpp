@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <numeric>
 #include <stdexcept>
 #include <utility>
@@ -17,6 +18,27 @@
 #include "host.hpp"
 
 namespace pamg {
+
+// An exception must not leave an OpenMP region (that is std::terminate, and the host process -- the Julia
+// session -- dies).  Loop bodies that can throw run under this guard: it keeps the first exception and
+// rethrows it after the region, where the C ABI's guard() turns it into a status code.
+namespace {
+struct OmpGuard {
+  std::exception_ptr ep;
+  template <class F>
+  void run(F&& f) noexcept {
+    try {
+      f();
+    } catch (...) {
+#pragma omp critical(pamg_omp_guard)
+      if (!ep) ep = std::current_exception();
+    }
+  }
+  void rethrow() {
+    if (ep) std::rethrow_exception(ep);
+  }
+};
+}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // partition  (PartitionedArrays uniform_partition / local_range, App. A)
@@ -941,8 +963,11 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     int kdof = 1;
     cur.agg_loc.resize(n);
     if (!use_ns) {
+      OmpGuard og;
 #pragma omp parallel for schedule(dynamic, 1)
-      for (int32_t p = 0; p < nparts; ++p) counts[p] = aggregate_part(cur.A, cur.owner, cur.oi, p, eps, absdiag, aggs[p]);
+      for (int32_t p = 0; p < nparts; ++p)
+        og.run([&] { counts[p] = aggregate_part(cur.A, cur.owner, cur.oi, p, eps, absdiag, aggs[p]); });
+      og.rethrow();
       for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
       nc = off[nparts];
       if (nc >= n) break;
@@ -975,8 +1000,10 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       OwnIndex oin;
       build_own_index(owner_node, nparts, oin);
       std::vector<double> none;
+      OmpGuard og;
 #pragma omp parallel for schedule(dynamic, 1)
-      for (int32_t p = 0; p < nparts; ++p) counts[p] = aggregate_part(N, owner_node, oin, p, 0.0, none, aggs[p]);
+      for (int32_t p = 0; p < nparts; ++p) og.run([&] { counts[p] = aggregate_part(N, owner_node, oin, p, 0.0, none, aggs[p]); });
+      og.rethrow();
       for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
       const int64_t nagg = off[nparts];
       nc = nagg * kdof;
@@ -1033,16 +1060,20 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     lev.rho = g[l].rho;
     lev.omega_p = g[l].omega_p;
     lev.parts.resize(nparts);
+    OmpGuard og;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int32_t p = 0; p < nparts; ++p) {
-      index_maps(g[l].A, g[l].owner, g[l].oi, p, lev.parts[p]);
-      gl[l][p].build(lev.parts[p].ghost_to_global);
-    }
+    for (int32_t p = 0; p < nparts; ++p)
+      og.run([&] {
+        index_maps(g[l].A, g[l].owner, g[l].oi, p, lev.parts[p]);
+        gl[l][p].build(lev.parts[p].ghost_to_global);
+      });
+    og.rethrow();
   }
   for (int32_t l = 0; l < L; ++l) {
     Level& lev = h.levels[l];
+    OmpGuard og;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int32_t p = 0; p < nparts; ++p) {
+    for (int32_t p = 0; p < nparts; ++p) og.run([&] {
       PartLevel& pl = lev.parts[p];
       split_blocks(g[l].A, pl.own_to_global, g[l].owner, g[l].oi.lid, p, pl.n_own, pl.n_ghost, gl[l][p],
                    pl.blk[PAMG_A_OO], pl.blk[PAMG_A_OG]);
@@ -1058,7 +1089,8 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
         pl.agg_local.resize(pl.n_own);
         for (int64_t i = 0; i < pl.n_own; ++i) pl.agg_local[i] = g[l].agg_loc[pl.own_to_global[i]];
       }
-    }
+    });
+    og.rethrow();
     build_halo_plans(lev, nparts);
   }
   tm.lap("localisation", L - 1);

@@ -33,7 +33,7 @@ namespace pamg {
 constexpr int RED_W = 4;  // doubles per all-reduce slot
 constexpr int MAX_LEVELS = 16;
 constexpr int BLOCK = 256;
-constexpr unsigned long long SPIN_TIMEOUT_NS = 2000000000ull;  // 2 s, then flag an error and fall through
+constexpr unsigned long long SPIN_TIMEOUT_NS = 20000000000ull;  // default 20 s (env PAMG_SPIN_TIMEOUT_MS): then error + done
 
 enum Mode : int { M_MUL = 0, M_RESID = 1, M_JACOBI = 2, M_ADD = 3, M_RESTRICT = 4, M_CHEB = 5 };
 
@@ -74,6 +74,7 @@ struct DevState {
   double sc[SC_COUNT];
   double dot_main;  // split launches: partial of the main launch, completed and published by k_boundary
   uint32_t check_seq;  // k_check executions since k_pcg_init
+  unsigned long long spin_timeout_ns;  // cross-GPU waits give up after this long (sets error and done)
   unsigned long long* trace;  // != nullptr: CTA 0 of every kernel appends its start time (globaltimer, ns)
   uint32_t trace_pos, trace_cap;
 };
@@ -173,8 +174,9 @@ __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t e, Dev
   const unsigned long long t0 = globaltimer_ns();
   while ((int32_t)(ld_acquire_sys(flag) - e) < 0) {
     if (*(volatile int32_t*)&st->error) return;
-    if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
-      st->error = 1;
+    if (globaltimer_ns() - t0 > st->spin_timeout_ns) {
+      st->error = 1;  // reported by the host after the call; `done` turns every later kernel of the solve into a no-op
+      st->done = 1;
       __threadfence();
       return;
     }
@@ -784,16 +786,17 @@ __global__ void __launch_bounds__(BLOCK) k_halo_unpack(double* __restrict__ dst,
 
 // assemble!: ghost -> owner.  Pack: this part's ghost values go to the owners' assemble staging.
 struct AsmSendNbr {
-  double* stage;   // owner's staging, offset to this part's segment
-  uint32_t* flag;  // owner's flag for this part
+  double* stage[2];  // owner's staging (double-buffered by epoch parity like the halo), offset to this part's segment
+  uint32_t* flag;    // owner's flag for this part
   int32_t slot0, count;
 };
 __global__ void __launch_bounds__(BLOCK) k_asm_pack(const double* __restrict__ ghost_vals, const AsmSendNbr* __restrict__ nbrs,
                                                      int n_nbrs, DevState* st, int level) {
   const uint32_t e = *(volatile uint32_t*)&st->asm_epoch[level] + 1u;
+  const int par = (int)(e & 1u);
   for (int nb = 0; nb < n_nbrs; ++nb)
     for (int k = blockIdx.x * BLOCK + threadIdx.x; k < nbrs[nb].count; k += gridDim.x * BLOCK)
-      nbrs[nb].stage[k] = ghost_vals[nbrs[nb].slot0 + k];
+      nbrs[nb].stage[par][k] = ghost_vals[nbrs[nb].slot0 + k];
   __threadfence_system();
   if (last_block(&st->ticket[2])) {
     __threadfence_system();
@@ -805,13 +808,16 @@ __global__ void __launch_bounds__(BLOCK) k_asm_pack(const double* __restrict__ g
 // ascending slot => deterministic), then the caller zeroes the ghosts.
 __global__ void __launch_bounds__(BLOCK) k_asm_add(double* __restrict__ own, const int32_t* __restrict__ rows,
                                                     const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
-                                                    int n_rows, const double* __restrict__ stage, const uint32_t* flags,
+                                                    int n_rows, const double* stage0, const double* stage1, const uint32_t* flags,
                                                     int n_flags, DevState* st, int level) {
+  __shared__ int s_par;
   if (threadIdx.x == 0) {
     const uint32_t e = *(volatile uint32_t*)&st->asm_epoch[level];
     for (int k = 0; k < n_flags; ++k) spin_until(flags + k, e, st);
+    s_par = (int)(e & 1u);
   }
   __syncthreads();
+  const double* stage = s_par ? stage1 : stage0;
   for (int r = blockIdx.x * BLOCK + threadIdx.x; r < n_rows; r += gridDim.x * BLOCK) {
     double s = own[rows[r]];
     for (int k = ptr[r]; k < ptr[r + 1]; ++k) s += __ldcv(stage + src[k]);
