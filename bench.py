@@ -188,7 +188,9 @@ def write_trace(c, part, path):
 
 def small_parity(rank, world, local_rank, nparts):
     """40^3 Poisson on the same N ranks (one part per GPU, CUDA-IPC peer memory, fused halo roles) against the oracle's
-    N-part V-cycle / PCG on the same operators.  Returns the record on every rank (max / min over ranks)."""
+    N-part V-cycle / PCG on the same operators, twice: with AUTO formats (CSR-stream at this size, everything below level 0
+    in the fused replicated tail) and with SELL-C-sigma forced and the coarse levels kept distributed (tail_rows = 600), i.e.
+    the kernel family and halo roles the 256^3 production run uses.  Returns the record on every rank (max over ranks)."""
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -197,38 +199,46 @@ def small_parity(rank, world, local_rank, nparts):
     from parallel_amg_b200.distributed import connect_parts
     dims = (40, 40, 40)
     L.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
-    c = L.Context(nparts)
-    c.gallery_poisson(dims, PARTS[nparts])
-    c.setup()
-    if world > 1:
-        connect_parts(c, rank, world, local_rank)
-    else:
-        c.device_init([0], [local_rank])
-    co = c_oracle.COracle.from_product_context(c, nparts)
-    n, _ = c.global_size()
-    own = [c.index_maps(0, p)[0] for p in range(nparts)]
-    me = rank if world > 1 else 0
-    v = xstar(n)[::-1].copy()
-    z_ref = co.vcycle([v[o] for o in own])
-    z = c.vcycle([v[own[p]] if p == me else None for p in range(nparts)])
-    scale = max(float(np.abs(r).max()) for r in z_ref)
-    err = float(np.abs(z[me] - z_ref[me]).max()) / scale
-    rhs = c.host_matvec_global(xstar(n))
-    x_ref, it_ref, hist_ref = co.pcg([rhs[o] for o in own], RTOL, MAXITER, True)
-    x, it, hist, ok = c.pcg([rhs[own[p]] if p == me else None for p in range(nparts)], RTOL, MAXITER, True)
-    match = bool(ok and it == it_ref and len(hist) == len(hist_ref) and np.allclose(hist, hist_ref, rtol=1e-7))
-    xerr = float(np.abs(x[me] - x_ref[me]).max())
-    fused = int(c.stats().fused_halo)
-    if world > 1:
-        t = torch.tensor([err, xerr, 0.0 if match else 1.0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        err, xerr, bad = [float(a) for a in t.cpu()]
-        match = bad == 0.0
-        dist.barrier()
-    co.close()
-    c.close()
-    return dict(problem="poisson3d-40", n_parts=nparts, vcycle_rel_err=err, iters=int(it), oracle_iters=int(it_ref), iters_match=match,
-                solution_max_abs_err=xerr, fused_halo=fused, tol_vcycle=1e-12)
+    rec = dict(problem="poisson3d-40", n_parts=nparts, tol_vcycle=1e-12, vcycle_rel_err=0.0, solution_max_abs_err=0.0, iters_match=True,
+               variants=[])
+    for vname, kopts in (("auto", {}), ("sell-distributed", dict(spmv_format=L.FORMAT_SELL, tail_rows=600))):
+        c = L.Context(nparts)
+        c.gallery_poisson(dims, PARTS[nparts])
+        c.setup(c.default_options(**kopts))
+        if world > 1:
+            connect_parts(c, rank, world, local_rank)
+        else:
+            c.device_init([0], [local_rank])
+        co = c_oracle.COracle.from_product_context(c, nparts)
+        n, _ = c.global_size()
+        own = [c.index_maps(0, p)[0] for p in range(nparts)]
+        me = rank if world > 1 else 0
+        v = xstar(n)[::-1].copy()
+        z_ref = co.vcycle([v[o] for o in own])
+        z = c.vcycle([v[own[p]] if p == me else None for p in range(nparts)])
+        scale = max(float(np.abs(r).max()) for r in z_ref)
+        err = float(np.abs(z[me] - z_ref[me]).max()) / scale
+        rhs = c.host_matvec_global(xstar(n))
+        x_ref, it_ref, hist_ref = co.pcg([rhs[o] for o in own], RTOL, MAXITER, True)
+        x, it, hist, ok = c.pcg([rhs[own[p]] if p == me else None for p in range(nparts)], RTOL, MAXITER, True)
+        match = bool(ok and it == it_ref and len(hist) == len(hist_ref) and np.allclose(hist, hist_ref, rtol=1e-7))
+        xerr = float(np.abs(x[me] - x_ref[me]).max())
+        stt = c.stats()
+        if world > 1:
+            t = torch.tensor([err, xerr, 0.0 if match else 1.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            err, xerr, bad = [float(a) for a in t.cpu()]
+            match = bad == 0.0
+            dist.barrier()
+        rec["variants"].append(dict(name=vname, vcycle_rel_err=err, iters=int(it), oracle_iters=int(it_ref), iters_match=match,
+                                    solution_max_abs_err=xerr, fused_halo=int(stt.fused_halo), tail_level=int(stt.tail_level),
+                                    format_A0=int(stt.format[0])))
+        rec["vcycle_rel_err"] = max(rec["vcycle_rel_err"], err)
+        rec["solution_max_abs_err"] = max(rec["solution_max_abs_err"], xerr)
+        rec["iters_match"] = bool(rec["iters_match"] and match)
+        co.close()
+        c.close()
+    return rec
 
 
 def measure(workload, args, rank, world, local_rank, steps, warmup, headline):

@@ -79,6 +79,7 @@ struct DevCsr {
   int nslices = 0, sell_rpt = 0, sell_sigma = 1;  // sell_rpt != 0 <=> the SELL kernel runs this block
   bool sell_perm = false;
   double sell_fill = 1.0;  // stored entries / nnz
+  bool short_rows = false; // no row has more than 8 entries (prolongators): eligible for the short-row instantiations
   CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
   StreamView sview() const { return StreamView{blk.p, ptr.p, col.p, val.p, nrows, nblocks}; }
   SellView slview() const { return SellView{sl_off.p, sl_col.p, sl_val.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
@@ -176,7 +177,8 @@ int pick_lanes(double mean) {
 }
 
 // fmt: PAMG_FORMAT_* requested for this block (own-ghost blocks are always compressed-row CSR)
-void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, int fmt, const pamg_options& o, int which) {
+void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, int fmt, const pamg_options& o, int which,
+               int rpt_override = 0) {
   const int64_t nr = m.nrows;
   std::vector<int32_t> ptr;
   d.listed = compress;
@@ -184,6 +186,12 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
   d.stream = false;
   d.nblocks = 0;
   d.sell_rpt = 0;
+  d.short_rows = false;
+  if (!m.ptr.empty()) {
+    int64_t mx = 0;
+    for (int64_t i = 0; i < nr; ++i) mx = std::max(mx, m.ptr[i + 1] - m.ptr[i]);
+    d.short_rows = mx <= 8;
+  }
   if (m.ptr.empty()) {  // absent block
     d.nrows = compress ? 0 : (int32_t)nr;
     ptr.assign((compress ? 0 : nr) + 1, 0);
@@ -218,20 +226,23 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     if (which == PAMG_R_OO) auto_sell = nr >= SELL_AUTO_MIN_ROWS_R;
   }
   if (!compress && nr > 0 && (fmt == PAMG_FORMAT_SELL || auto_sell)) {
-    const int rpt = (o.sell_rows_per_thread == 1 || o.sell_rows_per_thread == 2) ? o.sell_rows_per_thread : 2;
+    const int rpt = (o.sell_rows_per_thread == 1 || o.sell_rows_per_thread == 2) ? o.sell_rows_per_thread
+                    : (rpt_override == 1 && d.short_rows)                             ? 1
+                                                                                      : 2;
     const int C = 32 * rpt;
     SellHost sh;
     int sigma = o.sell_sigma > 0 ? o.sell_sigma : 1;
     sell_layout(m, C, sigma, sh, false);
     // auto sigma: sort inside windows only when the unsorted padding is large (the permutation costs more than
     // ~20 % padding does: P at 256^3 runs 0.228 ms unsorted with 1.16x fill, 0.240 ms sorted with 1.01x)
-    if (o.sell_sigma <= 0 && sh.fill > 1.25) {
+    const double sort_fill = getenv("PAMG_SELL_SORT_FILL") ? atof(getenv("PAMG_SELL_SORT_FILL")) : 1.25;
+    if (o.sell_sigma <= 0 && sh.fill > sort_fill) {
       SellHost s2;
       sell_layout(m, C, 64 * C, s2, false);
       if (s2.fill < sh.fill - 0.02) sigma = 64 * C;
       sh.fill = std::min(sh.fill, s2.fill);
     }
-    const bool take = fmt == PAMG_FORMAT_SELL || sh.fill <= SELL_AUTO_MAX_FILL;
+    const bool take = fmt == PAMG_FORMAT_SELL || sh.fill <= std::max(SELL_AUTO_MAX_FILL, sort_fill);
     if (take) {
       sell_layout(m, C, sigma, sh, true);
       d.sl_off.upload(sh.off);
@@ -271,6 +282,90 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
       d.stream = true;
     }
   }
+}
+
+// ---- upload-time renumbering of the own rows of a coarse level -------------------------------------------------------
+// SELL stores max-row-length entries for every row of a 64-row slice.  On the coarse levels of smoothed aggregation the row
+// lengths of A vary with the position of the aggregate (256^3, level 1: 8 .. 47 entries, mean 31), so consecutive rows pad
+// each other: 1.16x stored entries, and the level-1 sweeps were traffic-bound at 0.80 of the roofline (ncu r01).  A run-time
+// row permutation inside the kernel costs more than it saves (scattered epilogue accesses), so the own rows of a level >= 1
+// are RENUMBERED once at upload: sorted by row length inside windows of a few thousand rows, the same permutation applied to
+// A's rows and columns, P_{l-1}'s columns, R_{l-1}'s rows, P_l's rows, R_l's columns, the smoother weights, the halo send
+// lists and the tail gather map.  Entry order inside a row is kept, so every row sum adds the same products in the same
+// order: results are unchanged bit for bit; only the (internal) position of a row in the device vectors moves.  Host
+// vectors of such a level are permuted in upload_vec / download_vec.  Level 0 is never renumbered (PCG vectors, b and x).
+struct Renumbering {
+  std::vector<int32_t> old_of_new, new_of_old;  // empty: identity
+  bool active() const { return !old_of_new.empty(); }
+};
+
+double sell_fill_of(const std::vector<int32_t>& len, const std::vector<int32_t>* order, int C) {
+  const int64_t n = (int64_t)len.size();
+  int64_t stored = 0, nnz = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += C) {
+    int32_t w = 0;
+    for (int64_t k = s0; k < std::min<int64_t>(n, s0 + C); ++k) {
+      const int32_t v = len[order ? (*order)[k] : k];
+      w = std::max(w, v);
+      nnz += v;
+    }
+    stored += (int64_t)w * C;
+  }
+  return nnz ? (double)stored / (double)nnz : 1.0;
+}
+
+// key: A's row length first, then R_{l-1}'s and P_l's (their rows are this level's rows too), so that one permutation
+// serves the three operators as far as their lengths correlate
+void plan_renumbering(const PartLevel& pl, const PartLevel* finer, int C, int window, Renumbering& rn) {
+  rn = Renumbering();
+  const int64_t n = pl.n_own;
+  const LocalCsr& A = pl.blk[PAMG_A_OO];
+  if (A.ptr.empty() || n < 4 * C) return;
+  std::vector<int32_t> lenA(n), order(n);
+  std::vector<int64_t> key(n);
+  for (int64_t i = 0; i < n; ++i) {
+    lenA[i] = (int32_t)(A.ptr[i + 1] - A.ptr[i]);
+    int64_t lr = 0, lp = 0;
+    if (finer && !finer->blk[PAMG_R_OO].ptr.empty()) lr = finer->blk[PAMG_R_OO].ptr[i + 1] - finer->blk[PAMG_R_OO].ptr[i];
+    if (!pl.blk[PAMG_P_OO].ptr.empty()) lp = pl.blk[PAMG_P_OO].ptr[i + 1] - pl.blk[PAMG_P_OO].ptr[i];
+    key[i] = ((int64_t)lenA[i] << 24) | (std::min<int64_t>(lr, 4095) << 12) | std::min<int64_t>(lp, 4095);
+    order[i] = (int32_t)i;
+  }
+  const double fill0 = sell_fill_of(lenA, nullptr, C);
+  if (fill0 <= 1.03) return;
+  for (int64_t w0 = 0; w0 < n; w0 += window)
+    std::stable_sort(order.begin() + w0, order.begin() + std::min<int64_t>(n, w0 + window),
+                     [&](int32_t a, int32_t b) { return key[a] > key[b]; });
+  if (sell_fill_of(lenA, &order, C) > fill0 - 0.02) return;
+  rn.old_of_new = order;
+  rn.new_of_old.resize(n);
+  for (int64_t k = 0; k < n; ++k) rn.new_of_old[order[k]] = (int32_t)k;
+}
+
+// rows of m in the order `rows.old_of_new`, own columns relabelled through `cols.new_of_old`; entry order inside a row kept
+LocalCsr renumbered_block(const LocalCsr& m, const Renumbering* rows, const Renumbering* cols) {
+  if (m.ptr.empty()) return m;
+  const bool pr = rows && rows->active(), pc = cols && cols->active();
+  LocalCsr out;
+  out.nrows = m.nrows;
+  out.ncols = m.ncols;
+  out.ptr.assign(m.nrows + 1, 0);
+  for (int64_t k = 0; k < m.nrows; ++k) {
+    const int64_t i = pr ? rows->old_of_new[k] : k;
+    out.ptr[k + 1] = out.ptr[k] + (m.ptr[i + 1] - m.ptr[i]);
+  }
+  out.col.resize(m.col.size());
+  out.val.resize(m.val.size());
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < m.nrows; ++k) {
+    const int64_t i = pr ? rows->old_of_new[k] : k;
+    int64_t q = out.ptr[k];
+    for (int64_t e = m.ptr[i]; e < m.ptr[i + 1]; ++e, ++q) {
+      out.col[q] = pc ? cols->new_of_old[m.col[e]] : m.col[e];
+      out.val[q] = m.val[e];
+    }
+  }
+  return out;
 }
 
 // byte offsets inside a part's peer-visible arena; computable by every process for every part
@@ -357,6 +452,9 @@ struct PartDev {
   DBuf<double> xsol, p, q, bsave, hist, scratch4;
   DBuf<double> io_local;  // own+ghost staging for consistent!/assemble!
   DBuf<unsigned long long> trace;
+  std::vector<Renumbering> renum;  // per level: device numbering of the own rows (identity on level 0)
+  DBuf<TailOp> tail_ops;           // phases of the fused replicated tail (k_tail_fused), empty: multi-launch tail
+  int n_tail_ops = 0;
   int hist_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -379,6 +477,13 @@ struct Engine::Impl {
   int bnd_first = -1;       // block ids of a fused launch: 1 [pack | boundary | main], 0 [pack | main | boundary], -1 by size
   bool persistent = true;   // SELL / CSR-stream main roles run as one resident wave (env PAMG_PERSISTENT=0: one CTA per work item)
   bool fused_halo = false;  // every local part has a GPU of its own: halo roles run inside the consuming kernel
+  bool alone = false;       // every local part has a GPU of its own (a kernel may wait for its peers)
+  bool fused_tail = true;   // replicated tail as ONE persistent kernel (env PAMG_FUSED_TAIL=0: one launch per operation)
+  int tail_ctas = 2 * 148;  // its grid (env PAMG_TAIL_CTAS), capped by the occupancy limit: all CTAs must be resident
+  std::vector<std::vector<TailOp>>* tail_rec = nullptr;  // != nullptr: enqueue_* record tail phases instead of launching
+  bool unified = true;      // fused persistent SELL launches run without role CTAs (env PAMG_UNIFIED=0: pack / boundary CTAs)
+  bool fold_check = false;  // the convergence check runs inside k_update_xr / k_pcg_init (every local part alone on its GPU)
+  int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
   bool counting = true;
   // exchange needed per level/operator (decided on global metadata so every part agrees)
@@ -535,10 +640,39 @@ void launch_stream(int mode, bool dot, StreamView A, const LaunchArgs& L) {
   });
 }
 
-void launch_sell(int mode, bool dot, int rpt, SellView A, const LaunchArgs& L) {
+// short_variant (operators whose rows have at most 8 entries, i.e. the prolongators; M_ADD only): 0 = the A kernel,
+// 1 = <RPT 2, U 2, 5 CTAs/SM>, 2 = <RPT 1, U 4, 6 CTAs/SM> (needs the C = 32 layout).
+// try_unified: fused launch of one part per GPU -- run without role CTAs when every CTA's share of the boundary rows fits
+// (kernels.cuh "Unified CTA roles"); *was_unified reports the decision.
+void launch_sell(int mode, bool dot, int rpt, int short_variant, SellView A, LaunchArgs L, bool try_unified, bool* was_unified) {
   dispatch_mode(mode, dot, [&](auto md, auto dt) {
-    auto k = rpt == 2 ? k_spmv_sell<2, decltype(md)::value, decltype(dt)::value> : k_spmv_sell<1, decltype(md)::value, decltype(dt)::value>;
-    k<<<main_grid(L, (const void*)k), BLOCK, 0, L.s>>>(A, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
+    constexpr int MD = decltype(md)::value;
+    constexpr bool DT = decltype(dt)::value;
+    using Kern = void (*)(SellView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
+    Kern k = rpt == 2 ? (Kern)k_spmv_sell<2, MD, DT> : (Kern)k_spmv_sell<1, MD, DT>;
+    if constexpr (MD == M_ADD && !DT) {
+      if (short_variant == 1 && rpt == 2) k = (Kern)k_spmv_sell<2, M_ADD, false, 2, 5>;
+      if (short_variant == 2 && rpt == 1) k = (Kern)k_spmv_sell<1, M_ADD, false, 4, 6>;
+    }
+    int grid = 0;
+    *was_unified = false;
+    if (try_unified && rpt == 2) {
+      k = (Kern)k_spmv_sell_uni<MD, DT>;
+      const int n_work = std::max(1, std::min(L.grid, std::min(resident_ctas((const void*)k), RED_GRID)));
+      const int share = (L.fh.B.n + n_work - 1) / n_work;
+      if (share > BLOCK) {  // too many boundary rows for one resident wave: role CTAs
+        k = (Kern)k_spmv_sell<2, MD, DT>;
+      } else {
+        L.fh.unified = 1;
+        L.fh.bnd_share = std::max(share, 1);
+        if (L.fh.n_pack > 0) L.fh.n_pack = n_work;
+        if (L.fh.n_bnd > 0) L.fh.n_bnd = n_work;
+        grid = n_work;
+        *was_unified = true;
+      }
+    }
+    if (!grid) grid = main_grid(L, (const void*)k);
+    k<<<grid, BLOCK, 0, L.s>>>(A, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
   });
 }
 
@@ -553,6 +687,8 @@ void launch_boundary(int mode, bool dot, const LaunchArgs& L) {
 // One SpMV-family operation over all local parts: consistent!(xin) + own rows of the operator.
 // which: PAMG_A_OO / PAMG_P_OO / PAMG_R_OO (the matching *_OG is implied).
 // row_level: level whose LevelDev holds the blocks; halo_level: level of the column partition.
+struct TailRecordAbort {};  // an operation of the tail has no phase form (format, smoother): keep the multi-launch tail
+
 struct OpSpec {
   int row_level, which, halo_level, mode;
   bool dot = false;
@@ -574,6 +710,20 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
   const bool exchange = need && !op.coarse_ghosts_local;
   const bool fused = I.fused_halo;
   const int wsel = op.which / 2;  // 0 A, 1 P, 2 R
+  if (I.tail_rec) {  // recording the phases of the fused tail kernel: merged levels, CSR-stream blocks, no halo, no dot
+    for (size_t i = 0; i < I.parts.size(); ++i) {
+      const DevCsr& m = I.LV(i, l).blk[op.which];
+      if (!I.tail_mode || !m.stream || op.dot) throw TailRecordAbort();
+      TailOp t{};
+      t.kind = T_STREAM;
+      t.mode = op.mode;
+      t.A = m.sview();
+      t.x = xin[i];
+      t.a = epi[i];
+      (*I.tail_rec)[i].push_back(t);
+    }
+    return;
+  }
 
   auto halo_args = [&](PartDev& pd, bool with_pack, bool with_bnd) {
     LevelDev& ld = I.LV(pd, l);
@@ -610,7 +760,8 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     // B200 (256^3): SELL Jacobi sweep 0.316 ms persistent vs 0.344 ms with one CTA per 8 slices.
     // Long rows (level >= 1, 30+ entries per row) lose 10 % that way: they keep one CTA per 8 slices.
     const double mean_nnz = m.nrows ? (double)m.nnz / m.nrows : 0.0;
-    const bool bounded = I.persistent && m.sell_rpt && mean_nnz <= 12.0;
+    const bool try_unified = fused && I.unified && m.sell_rpt && (fh.n_pack > 0 || fh.n_bnd > 0);
+    const bool bounded = I.persistent && m.sell_rpt && (mean_nnz <= 12.0 || try_unified);
     LaunchArgs L{0, bounded || op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
     L.fh.v = xin[i];
     int n_main;
@@ -622,8 +773,10 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
       n_main = I.grid_for(m.nrows, (BLOCK / m.lanes) * 4);
     }
     L.grid = std::max(n_main, 1);
+    bool was_unified = false;
     if (m.sell_rpt)
-      launch_sell(op.mode, op.dot, m.sell_rpt, m.slview(), L);
+      launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, m.slview(), L, try_unified,
+                  &was_unified);
     else if (m.stream)
       launch_stream(op.mode, op.dot, m.sview(), L);
     else
@@ -633,7 +786,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
       static const char* OPS[] = {"A", "P", "R"};
       I.names.push_back(std::string(m.sell_rpt ? "sell " : m.stream ? "stream " : "csr ") + MODES[op.mode] + (op.dot ? "+dot " : " ") +
                         OPS[wsel] + std::to_string(l) + (I.tail_mode ? " tail" : "") + (fh.n_pack ? " +pack" : "") +
-                        (fh.n_bnd ? " +bnd" : ""));
+                        (fh.n_bnd ? " +bnd" : "") + (was_unified ? " uni" : ""));
       I.naming = false;
       I.note_launch();
       I.naming = true;
@@ -707,6 +860,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   I.ipc.resize(I.nparts);
   I.have_ipc.assign(I.nparts, 0);
   const pamg_options& o = h->opts;
+  if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
 
   // global decisions (identical in every process because the metadata is replicated)
   I.need_halo_A.assign(I.L, 0);
@@ -784,33 +938,61 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     pd.scratch4.alloc(RED_W);
     int max_blocks = Impl::MAX_GRID;
 
+    // device numbering of the own rows of the levels >= 1 that will run in SELL (see "upload-time renumbering" above)
+    pd.renum.assign(I.L, Renumbering());
+    {
+      const char* re = getenv("PAMG_RENUMBER");
+      const char* we = getenv("PAMG_RENUMBER_WINDOW");
+      const int window = we ? std::max(64, atoi(we)) : 4096;
+      if (re && atoi(re) != 0)  // off by default: measured a net loss at 256^3 (profiles/r02_kernel_sweep.md)
+        for (int l = 1; l < I.L; ++l) {
+          const PartLevel& pl = h->levels[l].parts[part];
+          const bool sell = o.spmv_format == PAMG_FORMAT_SELL || (o.spmv_format == PAMG_FORMAT_AUTO && pl.n_own >= SELL_AUTO_MIN_ROWS_A);
+          if (sell) plan_renumbering(pl, &h->levels[l - 1].parts[part], 64, window, pd.renum[l]);
+        }
+    }
+
     for (int l = 0; l < I.L; ++l) {
       const PartLevel& pl = h->levels[l].parts[part];
       pd.lev.emplace_back(new LevelDev);
       LevelDev& ld = *pd.lev.back();
       ld.n_own = pl.n_own;
       ld.n_ghost = pl.n_ghost;
+      const Renumbering& rn = pd.renum[l];
+      const Renumbering* rnc = l + 1 < I.L ? &pd.renum[l + 1] : nullptr;  // numbering of the next coarser level
       for (int b = 0; b < 6; b += 2) {
         int lanes = 0;
         if (b == PAMG_A_OO && o.lanes_per_row > 0) lanes = o.lanes_per_row;
-        build_csr(pl.blk[b], false, ld.blk[b], lanes, o.spmv_format, o, b);
-        build_bnd(pl.blk[b], pl.blk[b + 1], ld.bnd[b / 2]);
+        // row / own-column numbering of this block: A (l, l), P (l, l+1), R (l+1, l); ghost columns are staging slots
+        const Renumbering* rows = b == PAMG_R_OO ? rnc : &rn;
+        const Renumbering* cols = b == PAMG_P_OO ? rnc : &rn;
+        const bool moved = (rows && rows->active()) || (cols && cols->active());
+        LocalCsr t_oo, t_og;
+        if (moved) {
+          t_oo = renumbered_block(pl.blk[b], rows, cols);
+          t_og = renumbered_block(pl.blk[b + 1], rows, nullptr);
+        }
+        const LocalCsr& oo = moved ? t_oo : pl.blk[b];
+        const LocalCsr& og = moved ? t_og : pl.blk[b + 1];
+        build_csr(oo, false, ld.blk[b], lanes, o.spmv_format, o, b, b == PAMG_P_OO && I.p_kernel == 2 ? 1 : 0);
+        build_bnd(oo, og, ld.bnd[b / 2]);
         max_blocks = std::max(max_blocks, ld.blk[b].nblocks);
         max_blocks = std::max(max_blocks, (ld.blk[b].nslices + BLOCK / 32 - 1) / (BLOCK / 32));
       }
-      // smoother weights
+      // smoother weights (device numbering)
       std::vector<double> w(pl.n_own), dinv(pl.n_own);
       const double rho = h->levels[l].rho;
       const double lmax = o.cheb_hi_frac * rho, lmin = o.cheb_lo_frac * rho;
       const double theta = 0.5 * (lmax + lmin);
-      for (int64_t k = 0; k < pl.n_own; ++k) {
-        dinv[k] = 1.0 / pl.diag[k];
+      for (int64_t kn = 0; kn < pl.n_own; ++kn) {
+        const int64_t k = rn.active() ? rn.old_of_new[kn] : kn;
+        dinv[kn] = 1.0 / pl.diag[k];
         if (o.smoother == PAMG_SMOOTHER_L1JACOBI)
-          w[k] = 1.0 / pl.diag_l1[k];
+          w[kn] = 1.0 / pl.diag_l1[k];
         else if (o.smoother == PAMG_SMOOTHER_CHEBYSHEV)
-          w[k] = (1.0 / theta) / pl.diag[k];
+          w[kn] = (1.0 / theta) / pl.diag[k];
         else
-          w[k] = o.omega_jacobi / pl.diag[k];
+          w[kn] = o.omega_jacobi / pl.diag[k];
       }
       ld.w.upload(w);
       ld.dinv.upload(dinv);
@@ -822,7 +1004,13 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
         ld.d.alloc(pl.n_own);
         ld.d2.alloc(pl.n_own);
       }
-      ld.send_idx.upload(pl.send_idx);
+      if (rn.active()) {  // the halo pack gathers from device vectors
+        std::vector<int32_t> si(pl.send_idx.size());
+        for (size_t k = 0; k < si.size(); ++k) si[k] = rn.new_of_old[pl.send_idx[k]];
+        ld.send_idx.upload(si);
+      } else {
+        ld.send_idx.upload(pl.send_idx);
+      }
       ld.n_send = (int)pl.send_idx.size();
       ld.n_send_nbrs = (int)pl.send.size();
       ld.n_recv_nbrs = (int)pl.recv.size();
@@ -831,7 +1019,8 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       ld.hr.flags = (const uint32_t*)(pd.arena + pd.lay.flags[l]);
       ld.hr.n_nbrs = ld.n_recv_nbrs;
       // assemble! gather plan: for every own row that some neighbour holds as a ghost, the staging
-      // positions that contribute to it (ascending neighbour part, ascending slot)
+      // positions that contribute to it (ascending neighbour part, ascending slot).  It works on the caller's
+      // local vector (io_local), i.e. in the ORIGINAL numbering.
       {
         std::vector<std::vector<int32_t>> contrib(pl.n_own);
         for (size_t k = 0; k < pl.send_idx.size(); ++k) contrib[pl.send_idx[k]].push_back((int32_t)k);
@@ -881,7 +1070,13 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       }
     const PartLevel& pc = h->levels[I.tail_level].parts[part];
     pd.inv.upload(h->coarse_inv);
-    pd.own_gid_T.upload(pc.own_to_global);
+    {
+      const Renumbering& rt = pd.renum[I.tail_level];
+      std::vector<int64_t> og(pc.own_to_global);
+      if (rt.active())
+        for (size_t k = 0; k < og.size(); ++k) og[k] = pc.own_to_global[rt.old_of_new[k]];
+      pd.own_gid_T.upload(og);
+    }
     pd.ghost_gid_T.upload(pc.ghost_to_global);
     // PCG vectors on level 0
     const int64_t n0 = h->levels[0].parts[part].n_own;
@@ -921,15 +1116,55 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       throw CommError("halo plan: a part's send-neighbour set differs from its receive-neighbour set (structurally non-symmetric "
                       "operator); the peer-memory exchange protocol needs symmetric neighbour sets on multi-GPU layouts");
     if (const char* pe = getenv("PAMG_PERSISTENT")) I.persistent = atoi(pe) != 0;
+    if (const char* ue = getenv("PAMG_UNIFIED")) I.unified = atoi(ue) != 0;
+    if (const char* te = getenv("PAMG_FUSED_TAIL")) I.fused_tail = atoi(te) != 0;
+    if (const char* te = getenv("PAMG_TAIL_CTAS")) I.tail_ctas = std::max(1, atoi(te));
+    I.alone = alone;
+    {
+      const char* fe = getenv("PAMG_FOLD_CHECK");
+      I.fold_check = alone && (!fe || atoi(fe) != 0);
+    }
     if (const char* be = getenv("PAMG_BND_FIRST")) I.bnd_first = atoi(be) != 0 ? 1 : 0;
     const char* env = getenv("PAMG_FUSE_HALO");
     const bool want = env ? atoi(env) != 0 : o.fuse_halo != 0;
     I.fused_halo = want && alone && symmetric;
   }
+  build_tail_programs();
   if (nlocal == I.nparts) connect();
 }
 
 Engine::~Engine() { delete impl; }
+
+// The replicated tail as a list of phases for k_tail_fused: the V-cycle schedule of the merged levels is RECORDED by
+// running the ordinary enqueue code with Impl::tail_rec set, so the phase list follows nu_pre / nu_post / smoother /
+// buffer plan exactly as the multi-launch tail does.
+void Engine::build_tail_programs() {
+  Impl& I = *impl;
+  for (auto& up : I.parts) up->n_tail_ops = 0;
+  if (!I.fused_tail || I.tail_level >= I.L - 1 || I.h->opts.cycle != PAMG_CYCLE_V) return;
+  std::vector<std::vector<TailOp>> rec(I.parts.size());
+  I.tail_rec = &rec;
+  I.tail_mode = true;
+  bool ok = true;
+  try {
+    enqueue_vcycle(I.tail_level, false);
+  } catch (const TailRecordAbort&) {
+    ok = false;
+  } catch (...) {
+    I.tail_mode = false;
+    I.tail_rec = nullptr;
+    throw;
+  }
+  I.tail_mode = false;
+  I.tail_rec = nullptr;
+  if (!ok) return;
+  for (size_t i = 0; i < I.parts.size(); ++i) {
+    PartDev& pd = I.P(i);
+    I.set_dev(pd);
+    pd.tail_ops.upload(rec[i]);
+    pd.n_tail_ops = (int)rec[i].size();
+  }
+}
 
 // decide, per level, which buffer receives the zero-guess first sweep so that the V-cycle result
 // always ends in LevelDev::x whatever nu_pre / nu_post / Chebyshev degree are
@@ -1088,9 +1323,33 @@ void Engine::upload_vec(int level, const double* const* host, int which_buf) {
     PartDev& pd = *up;
     I.set_dev(pd);
     if (!host[pd.part]) throw std::runtime_error("null vector pointer for a local part");
+    const Renumbering& rn = pd.renum[level];
+    if (rn.active()) {  // host vectors are in the partition's numbering, device vectors of this level in the renumbered one
+      const int64_t n = pd.lev[level]->n_own;
+      std::vector<double> tmp(n);
+      for (int64_t k = 0; k < n; ++k) tmp[k] = host[pd.part][rn.old_of_new[k]];
+      CK(cudaMemcpyAsync(vec(pd, level, which_buf), tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, pd.stream));
+      CK(cudaStreamSynchronize(pd.stream));  // tmp goes out of scope
+      continue;
+    }
     CK(cudaMemcpyAsync(vec(pd, level, which_buf), host[pd.part], pd.lev[level]->n_own * sizeof(double), cudaMemcpyHostToDevice,
                        pd.stream));
   }
+}
+
+// device vector `src` of `level` (own length) -> host array in the partition's numbering; synchronous for renumbered levels
+void Engine::download_own(PartDev& pd, int level, const double* src, double* host) {
+  const Renumbering& rn = pd.renum[level];
+  const int64_t n = pd.lev[level]->n_own;
+  impl->set_dev(pd);
+  if (!rn.active()) {
+    CK(cudaMemcpyAsync(host, src, n * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
+    return;
+  }
+  std::vector<double> tmp(n);
+  CK(cudaMemcpyAsync(tmp.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
+  CK(cudaStreamSynchronize(pd.stream));
+  for (int64_t k = 0; k < n; ++k) host[rn.old_of_new[k]] = tmp[k];
 }
 
 void Engine::download_vec(int level, double* const* host, int which_buf) {
@@ -1099,8 +1358,7 @@ void Engine::download_vec(int level, double* const* host, int which_buf) {
     PartDev& pd = *up;
     I.set_dev(pd);
     if (!host[pd.part]) throw std::runtime_error("null vector pointer for a local part");
-    CK(cudaMemcpyAsync(host[pd.part], vec(pd, level, which_buf), pd.lev[level]->n_own * sizeof(double), cudaMemcpyDeviceToHost,
-                       pd.stream));
+    download_own(pd, level, vec(pd, level, which_buf), host[pd.part]);
   }
   sync_all();
 }
@@ -1228,13 +1486,50 @@ void Engine::enqueue_tail() {
   const int l = I.tail_level;
   const int n = (int)I.h->levels[l].n_global;
   const pamg_options& o = I.h->opts;
-  for (auto& up : I.parts) {
-    PartDev& pd = *up;
-    LevelDev& ld = *pd.lev[l];
-    I.set_dev(pd);
-    k_coarse_gather<<<I.grid_for(ld.n_own, BLOCK), BLOCK, 0, pd.stream>>>(ld.b.p, pd.own_gid_T.p, (int)ld.n_own, pd.coarse_pubs.p,
-                                                                         I.nparts, pd.st.p);
-    I.note_launch("k_coarse_gather");
+  bool fused_tail = l < I.L - 1;
+  for (auto& up : I.parts) fused_tail = fused_tail && up->n_tail_ops > 0;
+  const bool fold_gather = fused_tail && I.alone;  // the all-gather is phase 0 of the fused kernel
+  if (!fold_gather)
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& ld = *pd.lev[l];
+      I.set_dev(pd);
+      k_coarse_gather<<<I.grid_for(ld.n_own, BLOCK), BLOCK, 0, pd.stream>>>(ld.b.p, pd.own_gid_T.p, (int)ld.n_own, pd.coarse_pubs.p,
+                                                                           I.nparts, pd.st.p);
+      I.note_launch("k_coarse_gather");
+    }
+  if (fused_tail) {
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& ld = *pd.lev[l];
+      LevelDev& tl = *pd.tlev[l];
+      I.set_dev(pd);
+      TailIO io{};
+      io.g0 = (const double*)(pd.arena + pd.lay.coarse);
+      io.g1 = io.g0 + n;
+      io.flags = (const uint32_t*)(pd.arena + pd.lay.coarse_flags);
+      io.pubs = pd.coarse_pubs.p;
+      io.b_own = ld.b.p;
+      io.own_gid = pd.own_gid_T.p;
+      io.ghost_gid = pd.ghost_gid_T.p;
+      io.nparts = I.nparts;
+      io.n_own = (int32_t)ld.n_own;
+      io.n_ghost = (int32_t)ld.n_ghost;
+      io.n = n;
+      io.b_full = tl.b.p;
+      io.xstart = tl.xstart;
+      io.w = o.nu_pre > 0 ? tl.w.p : nullptr;
+      io.x_full = tl.x.p;
+      io.x_own = ld.x.p;
+      io.xg = (double*)ld.hr.ghost[0];
+      io.inv = pd.inv.p;
+      io.do_gather = fold_gather ? 1 : 0;
+      const int grid = std::max(1, std::min(I.tail_ctas, resident_ctas((const void*)k_tail_fused)));
+      k_tail_fused<<<grid, BLOCK, 0, pd.stream>>>(pd.tail_ops.p, pd.n_tail_ops, io, pd.st.p);
+      I.note_launch(fold_gather ? "k_tail_fused (gather + tail V-cycle + scatter)" : "k_tail_fused (tail V-cycle + scatter)");
+    }
+    CK(cudaGetLastError());
+    return;
   }
   if (l == I.L - 1) {
     for (auto& up : I.parts) {
@@ -1292,6 +1587,18 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
     return;
   }
   if (I.tail_mode && l == I.L - 1) {  // coarsest level of the replicated tail: x = A_L^-1 b, whole vector
+    if (I.tail_rec) {
+      for (size_t i = 0; i < np; ++i) {
+        LevelDev& ld = I.LV(i, l);
+        TailOp t{};
+        t.kind = T_DENSE;
+        t.x = ld.b.p;
+        t.a.out = ld.x.p;
+        t.n = (int32_t)ld.n_own;
+        (*I.tail_rec)[i].push_back(t);
+      }
+      return;
+    }
     for (auto& up : I.parts) {
       PartDev& pd = *up;
       LevelDev& ld = I.LV(pd, l);
@@ -1340,6 +1647,15 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
       for (size_t i = 0; i < np; ++i) {
         PartDev& pd = I.P(i);
         LevelDev& lc = I.LV(pd, l + 1);
+        if (I.tail_rec) {
+          TailOp t{};
+          t.kind = T_SCALE;
+          t.x = lc.b.p;
+          t.a.out = lc.xstart;
+          t.n = (int32_t)lc.n_own;
+          (*I.tail_rec)[i].push_back(t);
+          continue;
+        }
         I.set_dev(pd);
         k_scale<<<I.grid_for(lc.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(lc.b.p, nullptr, lc.xstart, (int)lc.n_own, pd.st.p);
         I.note_launch("k_scale");
@@ -1430,15 +1746,17 @@ void Engine::enqueue_pcg_iteration(bool precond) {
     I.set_dev(pd);
     k_update_xr<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.xsol.p, l0.b.p, pd.p.p, pd.q.p, l0.xstart,
                                                                          zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
-                                                                         pd.partials.p, pd.rc);
-    I.note_launch("k_update_xr");
+                                                                         pd.partials.p, pd.rc, I.fold_check ? 1 : 0, pd.hist.p,
+                                                                         up.get() == I.parts[0].get() ? I.hstat : nullptr);
+    I.note_launch(I.fold_check ? "k_update_xr+check" : "k_update_xr");
   }
-  for (auto& up : I.parts) {
-    PartDev& pd = *up;
-    I.set_dev(pd);
-    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
-    I.note_launch("k_check");
-  }
+  if (!I.fold_check)  // several parts on one GPU: a kernel must not wait for a later kernel of its own stream
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      I.set_dev(pd);
+      k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
+      I.note_launch("k_check");
+    }
   CK(cudaGetLastError());
 }
 
@@ -1530,7 +1848,7 @@ void Engine::smooth(int level, int nu, const double* const* b, double* const* x)
   for (size_t i = 0; i < I.parts.size(); ++i) {
     PartDev& pd = I.P(i);
     I.set_dev(pd);
-    CK(cudaMemcpyAsync(x[pd.part], cur[i], pd.lev[level]->n_own * sizeof(double), cudaMemcpyDeviceToHost, pd.stream));
+    download_own(pd, level, cur[i], x[pd.part]);
   }
   sync_all();
   check_device_error();
@@ -1778,15 +2096,17 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
     CK(cudaEventRecord(pd.ev0, pd.stream));
     k_pcg_init<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.bsave.p, pd.xsol.p, l0.b.p, pd.p.p, l0.xstart,
                                                                         zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
-                                                                        pd.partials.p, pd.rc, rtol, maxiter);
+                                                                        pd.partials.p, pd.rc, rtol, maxiter, I.fold_check ? 1 : 0,
+                                                                        pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
     I.note_launch("k_pcg_init");
   }
-  for (auto& up : I.parts) {
-    PartDev& pd = *up;
-    I.set_dev(pd);
-    k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
-    I.note_launch("k_check");
-  }
+  if (!I.fold_check)
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      I.set_dev(pd);
+      k_check<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.hist.p, up.get() == I.parts[0].get() ? I.hstat : nullptr);
+      I.note_launch("k_check");
+    }
   CK(cudaGetLastError());
   // speculative enqueue: iteration k+1 is launched before the status of iteration k is known; every
   // kernel early-outs once the device-side `done` flag is set, so the extra launch is a no-op.

@@ -62,10 +62,12 @@ class Engine {
   Impl* impl;
 
   void plan_buffers();
+  void build_tail_programs();
   void require_connected();
   void sync_all();
   void upload_vec(int level, const double* const* host, int which_buf);
   void download_vec(int level, double* const* host, int which_buf);
+  void download_own(PartDev& pd, int level, const double* src, double* host);
   double* vec(PartDev& pd, int level, int which);
   std::vector<const double*> ptrs(int level, int which);
   void check_device_error();

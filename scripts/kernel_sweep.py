@@ -39,10 +39,27 @@ CONFIGS = {
     "sell1-auto": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=1, sell_sigma=0),
     "sell2-auto": dict(spmv_format=L.FORMAT_SELL, sell_rows_per_thread=2, sell_sigma=0),
 }
+# A/B switches of the engine (read at device_init): name -> environment
+ENVS = {
+    "auto-r1": dict(PAMG_P_KERNEL="0", PAMG_RENUMBER="0"),       # round-1 behaviour
+    "auto-p0": dict(PAMG_P_KERNEL="0"),
+    "auto-p2": dict(PAMG_P_KERNEL="2"),
+    "auto-nore": dict(PAMG_RENUMBER="0"),
+    "auto-nosort": dict(PAMG_SELL_SORT_FILL="9"),
+    "auto-p2-nosort": dict(PAMG_P_KERNEL="2", PAMG_SELL_SORT_FILL="9"),
+    "auto-w16k": dict(PAMG_RENUMBER_WINDOW="16384"),
+}
+for k in ENVS:
+    CONFIGS[k] = dict(spmv_format=L.FORMAT_AUTO)
 if len(sys.argv) > 3:
     CONFIGS = {k: v for k, v in CONFIGS.items() if k in sys.argv[3].split(",")}
+else:
+    CONFIGS = {k: v for k, v in CONFIGS.items() if k not in ENVS}
 res = {}
 for name, kw in CONFIGS.items():
+    for k in ("PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW"):
+        os.environ.pop(k, None)
+    os.environ.update(ENVS.get(name, {}))
     c.set_kernel_options(**kw)
     c.device_init()
     c.load_rhs([b])

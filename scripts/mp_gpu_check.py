@@ -20,11 +20,25 @@ def main():
     from parallel_amg_b200.distributed import connect_parts
     from util import det_vector, product_options
     pp = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
-    cases = (((24, 20, 16), {}, {}), ((40, 40, 40), {}, {}), ((24, 20, 16), {"smoother": "chebyshev", "cheb_degree": 2}, {}),
-             ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL)), ((24, 20, 16), {}, dict(spmv_format=L.FORMAT_CSR)),
-             ((40, 40, 40), {"smoother": "l1jacobi"}, dict(spmv_format=L.FORMAT_SELL, sell_sigma=128, sell_rows_per_thread=1)),
-             ((24, 20, 16), {}, dict(fuse_halo=0)))
-    for dims, oopts, kopts in cases:
+    # (dims, oracle options, kernel options, environment switches of the engine)
+    cases = (((24, 20, 16), {}, {}, {}), ((40, 40, 40), {}, {}, {}), ((24, 20, 16), {"smoother": "chebyshev", "cheb_degree": 2}, {}, {}),
+             ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL), {}), ((24, 20, 16), {}, dict(spmv_format=L.FORMAT_CSR), {}),
+             ((40, 40, 40), {"smoother": "l1jacobi"}, dict(spmv_format=L.FORMAT_SELL, sell_sigma=128, sell_rows_per_thread=1), {}),
+             ((24, 20, 16), {}, dict(fuse_halo=0), {}),
+             # unified CTA roles (SELL, RPT 2) with distributed coarse levels, two sweeps, Chebyshev; role CTAs for comparison
+             ((40, 40, 40), {"nu_pre": 2, "nu_post": 2}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {}),
+             ((40, 40, 40), {"smoother": "chebyshev", "cheb_degree": 3}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {}),
+             ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {"PAMG_UNIFIED": "0"}),
+             ((48, 40, 36), {}, dict(spmv_format=L.FORMAT_SELL, sell_sigma=256, tail_rows=0), {}),
+             # replicated tail: one launch per operation / separate convergence check / renumbered coarse levels
+             ((40, 40, 40), {}, {}, {"PAMG_FUSED_TAIL": "0"}), ((40, 40, 40), {}, {}, {"PAMG_FOLD_CHECK": "0"}),
+             ((40, 40, 40), {"nu_pre": 0, "nu_post": 2}, {}, {}),
+             ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {"PAMG_RENUMBER": "1", "PAMG_RENUMBER_WINDOW": "256"}))
+    switches = ("PAMG_UNIFIED", "PAMG_FUSED_TAIL", "PAMG_FOLD_CHECK", "PAMG_RENUMBER", "PAMG_RENUMBER_WINDOW")
+    for dims, oopts, kopts, env in cases:
+        for k in switches:
+            os.environ.pop(k, None)
+        os.environ.update(env)
         A = O.poisson_fd(dims)
         owner = O.uniform_partition(pp, dims)
         h = O.build(A, owner, world, oopts)
@@ -67,6 +81,8 @@ def main():
         assert np.array_equal(loc[rank][len(mine):], b[lev["parts"][rank]["ghost_to_global"]])
         dist.barrier()
         c.close()
+        if rank == 0:
+            print("case ok", dims, oopts, {k: v for k, v in kopts.items()}, env, flush=True)
     if rank == 0:
         print("MP_GPU_OK", world, flush=True)
     dist.barrier()

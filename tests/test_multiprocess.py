@@ -35,10 +35,10 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
-@pytest.mark.timeout(400, method="thread")
+@pytest.mark.timeout(700, method="thread")
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs >= 2 GPUs (one rank per GPU; ranks must not share a device)")
 def test_one_rank_per_gpu_parity():
     world = 2 if _gpu_count() < 4 else 4
-    r = _torchrun(world, os.path.join(ROOT, "scripts", "mp_gpu_check.py"), 29533, 380)
+    r = _torchrun(world, os.path.join(ROOT, "scripts", "mp_gpu_check.py"), 29533, 680)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MP_GPU_OK" in r.stdout
