@@ -172,7 +172,8 @@ def write_trace(c, part, path):
     c.trace_enable(0)
     names = c.trace_names()
     k = len(names)
-    body = t[2:]                       # k_pcg_init, k_check, then `it` iterations of k kernels
+    head = len(t) - it * k if k else 0      # k_pcg_init (+ k_check when the check is not folded into it) precede the iterations
+    body = t[max(head, 0):]
     nit = min(it, len(body) // k) if k else 0
     with open(path, "w") as fh:
         fh.write(f"# iterations {it}, kernels per iteration {k}, records {len(t)}\n")

@@ -242,6 +242,13 @@ int pamg_vcycle(pamg_ctx* c, const double* const* b, double* const* x);
 int pamg_pcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter,
              int32_t precond, int32_t* iters, double* resid_hist);
 
+/* Flexible AMG-preconditioned CG (Notay): beta = z_{k+1}.(r_{k+1} - r_k) / (z_k.r_k).  Same arguments and results as
+ * pamg_pcg with precond = 1; it tolerates a preconditioner that is not a fixed SPD operator (W-cycles, truncated cycles).
+ * PartitionedSolvers has no separate entry point for it [RECALL-UNVERIFIED]; the oracle restatement is
+ * oracle/amg_oracle.py pcg(flexible=True) / pamg_oracle.c orc_pcg(precond = 2). */
+int pamg_fcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter, int32_t* iters,
+             double* resid_hist);
+
 /* ---- device-resident benchmarking hooks (inputs already in HBM) ------------------------
  * pamg_load_rhs copies b to the device once; pamg_pcg_resident re-solves from x=0 with the
  * resident b and leaves x on the device (pamg_read_solution fetches it). */

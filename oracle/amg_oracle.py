@@ -53,6 +53,7 @@ DEFAULTS = dict(
     cheb_degree=3,
     cheb_lo_frac=1.0 / 30.0,
     cheb_hi_frac=1.0,
+    cycle="v",            # "v" | "w": the coarse problem of a level is visited once / twice (second visit from the first's result)
     block_size=1,         # DOFs per node on level 0 (3 for elasticity); aggregation works on nodes
     nullspace=None,       # near-nullspace B (n x k, e.g. the 6 rigid-body modes): tentative P by per-aggregate QR
 )
@@ -850,14 +851,17 @@ def coarse_solve(h, bs):
     return pvector_from_global(level, x)
 
 
-def vcycle(h, bs, l=0):
-    """x = V(b) from x=0: pre-smooth, r=b-Ax, b_c=R r, recurse, x+=P e_c, post-smooth."""
+def vcycle(h, bs, l=0, xs0=None):
+    """x = cycle(b) from x = xs0 (0 by default): pre-smooth, r=b-Ax, b_c=R r, recurse, x+=P e_c, post-smooth.
+    opts["cycle"] == "w" (PartitionedSolvers `cycle = w_cycle`, App. A): the coarse problem A_c e_c = b_c is visited
+    twice, the second visit starting from the first one's e_c [DEFINED-HERE]; the coarsest level is solved exactly, so it
+    is visited once."""
     o = h["opts"]
     L = len(h["levels"])
     level = h["levels"][l]
     if l == L - 1:
         return coarse_solve(h, bs)
-    xs = pvector_zeros(level)
+    xs = pvector_zeros(level) if xs0 is None else [x.copy() for x in xs0]
     xs = smooth(h, l, xs, bs, o["nu_pre"])
     consistent(level, xs)
     rs = pvector_zeros(level)
@@ -871,6 +875,8 @@ def vcycle(h, bs, l=0):
         nc = len(dc["own_to_global"])
         bc[:nc] = _mul(d, "R", r, len(d["own_to_global"]))
     ecs = vcycle(h, bcs, l + 1)
+    if o["cycle"] == "w" and l + 1 < L - 1:
+        ecs = vcycle(h, bcs, l + 1, xs0=ecs)
     consistent(nxt, ecs)
     for d, dc, x, ec in zip(level["parts"], nxt["parts"], xs, ecs):
         n = len(d["own_to_global"])
@@ -884,9 +890,11 @@ def prepare(h):
     return h
 
 
-def pcg(h, bs, rtol=1e-8, maxiter=200, precond=True):
+def pcg(h, bs, rtol=1e-8, maxiter=200, precond=True, flexible=False):
     """Preconditioned CG, x0 = 0, stop at ||r|| <= rtol*||r0||.  Returns xs, iters, hist
-    (hist[0]=||r0||, hist[k]=||r_k||)."""
+    (hist[0]=||r0||, hist[k]=||r_k||).  flexible: Notay's flexible CG, beta = z_{k+1}.(r_{k+1} - r_k) / (z_k.r_k)
+    (Polak-Ribiere), which tolerates a preconditioner that changes between iterations (W-cycles with inexact coarse
+    solves, mixed precision); with a fixed SPD preconditioner it equals PCG in exact arithmetic."""
     level = h["levels"][0]
     xs = pvector_zeros(level)
     rs = [b.copy() for b in bs]
@@ -902,6 +910,7 @@ def pcg(h, bs, rtol=1e-8, maxiter=200, precond=True):
     while it < maxiter:
         qs = spmv(level, ps)
         alpha = rho / pdot(level, ps, qs)
+        rs_old = [r.copy() for r in rs] if flexible else None
         for x, r, p, q in zip(xs, rs, ps, qs):
             x += alpha * p
             r -= alpha * q
@@ -912,7 +921,7 @@ def pcg(h, bs, rtol=1e-8, maxiter=200, precond=True):
             break
         zs = M(rs)
         rho_new = pdot(level, rs, zs)
-        beta = rho_new / rho
+        beta = (rho_new - pdot(level, rs_old, zs)) / rho if flexible else rho_new / rho
         rho = rho_new
         ps = [z + beta * p for z, p in zip(zs, ps)]
     return xs, it, hist

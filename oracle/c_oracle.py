@@ -41,6 +41,8 @@ def _load():
     lib.orc_set_coarse.argtypes = [C.c_void_p, C.c_int64, _f64p, C.c_int32, _i64p, _i64p]
     lib.orc_destroy.restype = None
     lib.orc_destroy.argtypes = [C.c_void_p]
+    lib.orc_set_cycle.restype = None
+    lib.orc_set_cycle.argtypes = [C.c_void_p, C.c_int32]
     lib.orc_vcycle.restype = None
     lib.orc_vcycle.argtypes = [C.c_void_p, C.POINTER(_f64p), C.POINTER(_f64p)]
     lib.orc_pcg.restype = C.c_int32
@@ -59,12 +61,13 @@ class COracle:
 
     NAMES = ("A_oo", "A_og", "P_oo", "P_og", "R_oo", "R_og")
 
-    def __init__(self, levels, coarse_inv, nu_pre=1, nu_post=1):
+    def __init__(self, levels, coarse_inv, nu_pre=1, nu_post=1, cycle="v"):
         self.lib = _load()
         self.nparts = len(levels[0])
         self.L = len(levels)
         self.keep = []
         self.h = self.lib.orc_create(self.nparts, self.L, nu_pre, nu_post)
+        self.lib.orc_set_cycle(self.h, 1 if cycle == "w" else 0)
         self.n_own = [[len(d["own_to_global"]) for d in lev] for lev in levels]
         for l, lev in enumerate(levels):
             for p, d in enumerate(lev):
@@ -111,10 +114,10 @@ class COracle:
                 e["w"] = O._wdinv(d, h["opts"])
                 parts.append(e)
             levels.append(parts)
-        return cls(levels, h["coarse_inv"], h["opts"]["nu_pre"], h["opts"]["nu_post"])
+        return cls(levels, h["coarse_inv"], h["opts"]["nu_pre"], h["opts"]["nu_post"], h["opts"].get("cycle", "v"))
 
     @classmethod
-    def from_product_context(cls, ctx, nparts, nu_pre=1, nu_post=1, omega=2.0 / 3.0, smoother="jacobi"):
+    def from_product_context(cls, ctx, nparts, nu_pre=1, nu_post=1, omega=2.0 / 3.0, smoother="jacobi", cycle="v"):
         """The hierarchy the PRODUCT's host setup built, copied out through the C ABI queries (pamg_get_index_maps /
         pamg_get_block / pamg_get_diag / pamg_get_coarse_inverse), so that the oracle and the device run the same
         operators at sizes where the numpy oracle's own setup would take minutes.  ctx: parallel_amg_b200._lib.Context."""
@@ -135,7 +138,7 @@ class COracle:
                 d["w"] = (1.0 / dl1) if smoother == "l1jacobi" else omega / dg
                 parts.append(d)
             levels.append(parts)
-        return cls(levels, ctx.coarse_inverse(), nu_pre, nu_post)
+        return cls(levels, ctx.coarse_inverse(), nu_pre, nu_post, cycle)
 
     def _vecs(self, arrs):
         out = (_f64p * self.nparts)()
@@ -151,12 +154,13 @@ class COracle:
         self.lib.orc_vcycle(self.h, bp, zp)
         return k2
 
-    def pcg(self, b_parts, rtol=1e-8, maxiter=200, precond=True):
+    def pcg(self, b_parts, rtol=1e-8, maxiter=200, precond=True, flexible=False):
         x = [np.zeros(n) for n in self.n_own[0]]
         bp, k1 = self._vecs(b_parts)
         xp, k2 = self._vecs(x)
         hist = np.zeros(maxiter + 2)
-        it = self.lib.orc_pcg(self.h, bp, xp, float(rtol), int(maxiter), int(bool(precond)), _p(hist, C.c_double))
+        mode = 2 if (flexible and precond) else int(bool(precond))
+        it = self.lib.orc_pcg(self.h, bp, xp, float(rtol), int(maxiter), mode, _p(hist, C.c_double))
         return k2, int(it), hist[: it + 1].copy()
 
     def close(self):

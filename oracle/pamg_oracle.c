@@ -39,6 +39,7 @@ typedef struct {
 
 typedef struct {
   int32_t nparts, nlevels, nu_pre, nu_post;
+  int32_t cycle_w;            /* 1: W-cycle (amg_oracle.vcycle, opts["cycle"] == "w") */
   part_t* p;                  /* [nlevels][nparts] */
   int64_t n_coarse;
   const double* inv;          /* row-major, indexed by coarse gid */
@@ -91,6 +92,8 @@ void orc_set_coarse(orc_t* o, int64_t n, const double* inv, int32_t part, const 
   o->coarse_ggid[part] = ghost_gid;
   if (!o->cb) o->cb = (double*)calloc((size_t)n + 1, sizeof(double));
 }
+
+void orc_set_cycle(orc_t* o, int32_t w_cycle) { o->cycle_w = w_cycle; }
 
 void orc_destroy(orc_t* o) {
   if (!o) return;
@@ -179,8 +182,11 @@ static void coarse_solve(orc_t* o) {
   }
 }
 
-/* V-cycle from x = 0; rhs in part.b_, result in part.x (local, ghosts of the result are NOT consistent) */
-static void vcycle(orc_t* o, int l) {
+/* cycle from x = 0 (zero_guess) or from the current part.x; rhs in part.b_, result in part.x (local, ghosts of the
+ * result are NOT consistent).  W-cycle: the coarse problem is visited twice, the second time from the first result. */
+static void vcycle_from(orc_t* o, int l, int zero_guess);
+static void vcycle(orc_t* o, int l) { vcycle_from(o, l, 1); }
+static void vcycle_from(orc_t* o, int l, int zero_guess) {
   const int P = o->nparts;
   if (l == o->nlevels - 1) {
     coarse_solve(o);
@@ -193,7 +199,7 @@ static void vcycle(orc_t* o, int l) {
     nxt[q] = p->x2;
     bs[q] = p->b_;
     ts[q] = p->t;
-    memset(p->x, 0, sizeof(double) * (size_t)(p->n_own + p->n_ghost));
+    if (zero_guess) memset(p->x, 0, sizeof(double) * (size_t)(p->n_own + p->n_ghost));
   }
   for (int s = 0; s < o->nu_pre; ++s) {
     orc_jacobi(o, l, cur, bs, nxt);
@@ -218,7 +224,8 @@ static void vcycle(orc_t* o, int l) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < pc->n_own; ++i) bc[i] = row_mul(&p->b[4], &p->b[5], t, p->n_own, i);
   }
-  vcycle(o, l + 1);
+  vcycle_from(o, l + 1, 1);
+  if (o->cycle_w && l + 1 < o->nlevels - 1) vcycle_from(o, l + 1, 0);
   /* x += P e_c (coarse result is always in part.x of level l+1) */
   {
     double* ec[256];
@@ -270,10 +277,12 @@ static double pdot(orc_t* o, double** us, double** vs) {
 }
 
 /* PCG from x0 = 0; returns iterations; hist[0..iters]; x_parts own-length outputs. */
+/* precond: 0 plain CG, 1 PCG, 2 flexible PCG (beta = z_{k+1}.(r_{k+1} - r_k) / (z_k.r_k), amg_oracle.pcg flexible=True) */
 int32_t orc_pcg(orc_t* o, const double* const* b_parts, double* const* x_parts, double rtol, int32_t maxiter,
                 int32_t precond, double* hist) {
   const int P = o->nparts;
-  double *xs[256], *rs[256], *ps[256], *qs[256], *zs[256];
+  const int flexible = precond == 2;
+  double *xs[256], *rs[256], *ps[256], *qs[256], *zs[256], *ro[256];
   for (int q = 0; q < P; ++q) {
     part_t* p = &PART(o, 0, q);
     size_t nl = (size_t)(p->n_own + p->n_ghost) + 1;
@@ -282,6 +291,7 @@ int32_t orc_pcg(orc_t* o, const double* const* b_parts, double* const* x_parts, 
     ps[q] = (double*)calloc(nl, sizeof(double));
     qs[q] = (double*)calloc(nl, sizeof(double));
     zs[q] = (double*)calloc(nl, sizeof(double));
+    ro[q] = (double*)calloc(nl, sizeof(double));
     memcpy(rs[q], b_parts[q], sizeof(double) * (size_t)p->n_own);
   }
 #define APPLY_M()                                                                             \
@@ -310,6 +320,8 @@ int32_t orc_pcg(orc_t* o, const double* const* b_parts, double* const* x_parts, 
     while (it < maxiter) {
       orc_spmv(o, 0, ps, qs);
       const double alpha = rho / pdot(o, ps, qs);
+      if (flexible)
+        for (int q = 0; q < P; ++q) memcpy(ro[q], rs[q], sizeof(double) * (size_t)PART(o, 0, q).n_own);
       for (int q = 0; q < P; ++q) {
         part_t* p = &PART(o, 0, q);
         double *x = xs[q], *r = rs[q];
@@ -326,7 +338,7 @@ int32_t orc_pcg(orc_t* o, const double* const* b_parts, double* const* x_parts, 
       if (rn <= rtol * r0) break;
       APPLY_M();
       const double rho_new = pdot(o, rs, zs);
-      const double beta = rho_new / rho;
+      const double beta = flexible ? (rho_new - pdot(o, ro, zs)) / rho : rho_new / rho;
       rho = rho_new;
       for (int q = 0; q < P; ++q) {
         part_t* p = &PART(o, 0, q);
@@ -344,6 +356,7 @@ int32_t orc_pcg(orc_t* o, const double* const* b_parts, double* const* x_parts, 
     free(ps[q]);
     free(qs[q]);
     free(zs[q]);
+    free(ro[q]);
   }
   return it;
 }

@@ -749,7 +749,14 @@ int pamg_pcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol,
              int32_t* iters, double* resid_hist) {
   return guard(c, [&] {
     need(b && x && rtol >= 0.0 && maxiter >= 0, "bad arguments");
-    return engine(c).pcg(b, x, rtol, maxiter, precond != 0, iters, resid_hist);
+    return engine(c).pcg(b, x, rtol, maxiter, precond != 0 ? 1 : 0, iters, resid_hist);
+  });
+}
+int pamg_fcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter, int32_t* iters,
+             double* resid_hist) {
+  return guard(c, [&] {
+    need(b && x && rtol >= 0.0 && maxiter >= 0, "bad arguments");
+    return engine(c).pcg(b, x, rtol, maxiter, 2, iters, resid_hist);
   });
 }
 int pamg_load_rhs(pamg_ctx* c, const double* const* b) {
@@ -762,7 +769,7 @@ int pamg_load_rhs(pamg_ctx* c, const double* const* b) {
 int pamg_pcg_resident(pamg_ctx* c, double rtol, int32_t maxiter, int32_t precond, int32_t* iters, double* resid_hist) {
   return guard(c, [&] {
     need(rtol >= 0.0 && maxiter >= 0, "bad arguments");
-    return engine(c).pcg_resident(rtol, maxiter, precond != 0, iters, resid_hist);
+    return engine(c).pcg_resident(rtol, maxiter, precond != 0 ? 1 : 0, iters, resid_hist);
   });
 }
 int pamg_read_solution(pamg_ctx* c, double* const* x) {

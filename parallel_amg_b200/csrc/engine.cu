@@ -449,7 +449,7 @@ struct PartDev {
   DBuf<CoarsePub> coarse_pubs;
   DBuf<double> inv;
   DBuf<int64_t> own_gid_T, ghost_gid_T;
-  DBuf<double> xsol, p, q, bsave, hist, scratch4;
+  DBuf<double> xsol, p, q, bsave, hist, scratch4, rprev;  // rprev: r_k of flexible CG (allocated on first use)
   DBuf<double> io_local;  // own+ghost staging for consistent!/assemble!
   DBuf<unsigned long long> trace;
   std::vector<Renumbering> renum;  // per level: device numbering of the own rows (identity on level 0)
@@ -478,10 +478,10 @@ struct Engine::Impl {
   bool persistent = true;   // SELL / CSR-stream main roles run as one resident wave (env PAMG_PERSISTENT=0: one CTA per work item)
   bool fused_halo = false;  // every local part has a GPU of its own: halo roles run inside the consuming kernel
   bool alone = false;       // every local part has a GPU of its own (a kernel may wait for its peers)
-  bool fused_tail = true;   // replicated tail as ONE persistent kernel (env PAMG_FUSED_TAIL=0: one launch per operation)
+  bool fused_tail = false;  // replicated tail as ONE persistent kernel (env PAMG_FUSED_TAIL=1; measured slower than one launch per operation)
   int tail_ctas = 2 * 148;  // its grid (env PAMG_TAIL_CTAS), capped by the occupancy limit: all CTAs must be resident
   std::vector<std::vector<TailOp>>* tail_rec = nullptr;  // != nullptr: enqueue_* record tail phases instead of launching
-  bool unified = true;      // fused persistent SELL launches run without role CTAs (env PAMG_UNIFIED=0: pack / boundary CTAs)
+  int unified = 15;         // fused persistent SELL launches run without role CTAs: bit mask over operator classes (env PAMG_UNIFIED)
   bool fold_check = false;  // the convergence check runs inside k_update_xr / k_pcg_init (every local part alone on its GPU)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
@@ -492,7 +492,7 @@ struct Engine::Impl {
   std::vector<cudaGraphExec_t> g_iter, g_vcycle;
   std::vector<cudaStream_t> g_streams;
   int64_t g_iter_nodes = 0, g_vcycle_nodes = 0;
-  bool g_iter_precond = true;
+  int g_iter_mode = -1;  // mode the iteration graph was captured for: 0 plain CG, 1 PCG, 2 flexible PCG
   double* flush_buf = nullptr;
   size_t flush_n = 0;
   pamg_stats stats{};
@@ -760,7 +760,9 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     // B200 (256^3): SELL Jacobi sweep 0.316 ms persistent vs 0.344 ms with one CTA per 8 slices.
     // Long rows (level >= 1, 30+ entries per row) lose 10 % that way: they keep one CTA per 8 slices.
     const double mean_nnz = m.nrows ? (double)m.nnz / m.nrows : 0.0;
-    const bool try_unified = fused && I.unified && m.sell_rpt && (fh.n_pack > 0 || fh.n_bnd > 0);
+    // PAMG_UNIFIED bit mask: 1 = A with short rows, 2 = A with long rows, 4 = P, 8 = R
+    const int uni_bit = op.which == PAMG_P_OO ? 4 : op.which == PAMG_R_OO ? 8 : (mean_nnz <= 12.0 ? 1 : 2);
+    const bool try_unified = fused && (I.unified & uni_bit) && m.sell_rpt && (fh.n_pack > 0 || fh.n_bnd > 0);
     const bool bounded = I.persistent && m.sell_rpt && (mean_nnz <= 12.0 || try_unified);
     LaunchArgs L{0, bounded || op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
     L.fh.v = xin[i];
@@ -1116,7 +1118,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
       throw CommError("halo plan: a part's send-neighbour set differs from its receive-neighbour set (structurally non-symmetric "
                       "operator); the peer-memory exchange protocol needs symmetric neighbour sets on multi-GPU layouts");
     if (const char* pe = getenv("PAMG_PERSISTENT")) I.persistent = atoi(pe) != 0;
-    if (const char* ue = getenv("PAMG_UNIFIED")) I.unified = atoi(ue) != 0;
+    if (const char* ue = getenv("PAMG_UNIFIED")) I.unified = atoi(ue);
     if (const char* te = getenv("PAMG_FUSED_TAIL")) I.fused_tail = atoi(te) != 0;
     if (const char* te = getenv("PAMG_TAIL_CTAS")) I.tail_ctas = std::max(1, atoi(te));
     I.alone = alone;
@@ -1147,7 +1149,7 @@ void Engine::build_tail_programs() {
   I.tail_mode = true;
   bool ok = true;
   try {
-    enqueue_vcycle(I.tail_level, false);
+    enqueue_vcycle(I.tail_level, false, true);
   } catch (const TailRecordAbort&) {
     ok = false;
   } catch (...) {
@@ -1481,11 +1483,33 @@ void Engine::enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_
 // Levels [tail_level, L).  With only the coarsest level in the tail: all-gather b_L and apply the dense
 // inverse to this part's own + ghost rows.  Otherwise: all-gather b of the first tail level, run the
 // merged levels on this GPU alone (no halo), and scatter x back to this part's own + ghost slots.
-void Engine::enqueue_tail() {
+void Engine::enqueue_tail(bool zero_guess) {
   Impl& I = *impl;
   const int l = I.tail_level;
   const int n = (int)I.h->levels[l].n_global;
   const pamg_options& o = I.h->opts;
+  if (!zero_guess) {  // W-cycle, second visit: the right-hand side is unchanged, the merged level continues from its x
+    if (l == I.L - 1) return;  // exact solve: nothing to improve
+    I.tail_mode = true;
+    try {
+      enqueue_vcycle(l, false, false);
+    } catch (...) {
+      I.tail_mode = false;
+      throw;
+    }
+    I.tail_mode = false;
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& ld = *pd.lev[l];
+      LevelDev& tl = *pd.tlev[l];
+      I.set_dev(pd);
+      k_tail_out<<<I.grid_for(std::max<int64_t>(ld.n_own + ld.n_ghost, 1), BLOCK), BLOCK, 0, pd.stream>>>(
+          tl.x.p, pd.own_gid_T.p, (int)ld.n_own, pd.ghost_gid_T.p, (int)ld.n_ghost, ld.x.p, (double*)ld.hr.ghost[0], pd.st.p);
+      I.note_launch("k_tail_out");
+    }
+    CK(cudaGetLastError());
+    return;
+  }
   bool fused_tail = l < I.L - 1;
   for (auto& up : I.parts) fused_tail = fused_tail && up->n_tail_ops > 0;
   const bool fold_gather = fused_tail && I.alone;  // the all-gather is phase 0 of the fused kernel
@@ -1558,7 +1582,7 @@ void Engine::enqueue_tail() {
   CK(cudaGetLastError());
   I.tail_mode = true;
   try {
-    enqueue_vcycle(l, false);
+    enqueue_vcycle(l, false, true);
   } catch (...) {
     I.tail_mode = false;
     throw;
@@ -1578,12 +1602,13 @@ void Engine::enqueue_tail() {
 
 // V-cycle from level l.  Preconditions: lev[l].b holds the right-hand side and lev[l].xstart holds
 // the zero-guess first pre-smoothing step (w .* b, or 0 when nu_pre == 0).  Result in lev[l].x.
-void Engine::enqueue_vcycle(int l, bool dot_rz) {
+// zero_guess == false (W-cycle, second visit of a level): continue from the current lev[l].x with full pre-smoothing.
+void Engine::enqueue_vcycle(int l, bool dot_rz, bool zero_guess) {
   Impl& I = *impl;
   const pamg_options& o = I.h->opts;
   const size_t np = I.parts.size();
   if (!I.tail_mode && l == I.tail_level) {
-    enqueue_tail();
+    enqueue_tail(zero_guess);
     return;
   }
   if (I.tail_mode && l == I.L - 1) {  // coarsest level of the replicated tail: x = A_L^-1 b, whole vector
@@ -1613,8 +1638,8 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
   // the next level is entered through the tail gather / the dense solve: no fused zero-guess step for it
   const bool next_is_entry = I.tail_mode ? (l + 1 == I.L - 1) : (l + 1 == I.tail_level);
   std::vector<double*> cur(np);
-  for (size_t i = 0; i < np; ++i) cur[i] = I.LV(i, l).xstart;
-  if (o.nu_pre > 0) enqueue_smooth(l, o.nu_pre, cur, /*zero_guess_done=*/true, false);
+  for (size_t i = 0; i < np; ++i) cur[i] = zero_guess ? I.LV(i, l).xstart : I.LV(i, l).x.p;
+  if (o.nu_pre > 0) enqueue_smooth(l, o.nu_pre, cur, /*zero_guess_done=*/zero_guess, false);
   // residual t = b - A x
   {
     std::vector<EpiArgs> epi(np);
@@ -1661,7 +1686,9 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
         I.note_launch("k_scale");
       }
   }
-  enqueue_vcycle(l + 1, false);
+  enqueue_vcycle(l + 1, false, true);
+  // W-cycle: the coarse problem is visited a second time, from the first visit's result (the coarsest solve is exact)
+  if (o.cycle == PAMG_CYCLE_W && l + 1 < I.L - 1) enqueue_vcycle(l + 1, false, false);
   // prolongation + correction (out of place): nxt = cur + P e_c
   {
     std::vector<EpiArgs> epi(np);
@@ -1679,8 +1706,16 @@ void Engine::enqueue_vcycle(int l, bool dot_rz) {
     cur = nxt;
   }
   if (o.nu_post > 0) enqueue_smooth(l, o.nu_post, cur, false, dot_rz);
-  for (size_t i = 0; i < np; ++i)
-    if (cur[i] != I.LV(i, l).x.p) throw std::runtime_error("internal: V-cycle buffer plan mismatch");
+  for (size_t i = 0; i < np; ++i) {
+    LevelDev& ld = I.LV(i, l);
+    if (cur[i] == ld.x.p) continue;
+    if (zero_guess) throw std::runtime_error("internal: V-cycle buffer plan mismatch");
+    // a visit that started from x has one buffer flip more than the plan of the zero-guess visit: copy back
+    PartDev& pd = I.P(i);
+    I.set_dev(pd);
+    k_copy<<<I.grid_for(ld.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(cur[i], ld.x.p, (int)ld.n_own, pd.st.p);
+    I.note_launch("k_copy");
+  }
 }
 
 // r.z when the V-cycle could not fuse it (nu_post == 0, Chebyshev, or a single-level hierarchy)
@@ -1705,11 +1740,21 @@ bool Engine::vcycle_fuses_rz() const {
 // one PCG iteration (uniform body, see DESIGN.md "PCG schedule"):
 //   z = M^-1 r (rz fused) ; beta = rz/rho_old ; p = z + beta p ; q = A p (pq fused) ;
 //   alpha = rz/pq ; x += alpha p ; r -= alpha q ; z0 = w .* r ; rr ; check
-void Engine::enqueue_pcg_iteration(bool precond) {
+void Engine::enqueue_pcg_iteration(int mode) {
   Impl& I = *impl;
   const size_t np = I.parts.size();
-  if (precond) {
-    enqueue_vcycle(0, vcycle_fuses_rz());
+  const bool precond = mode != 0, flexible = mode == 2;
+  if (flexible) {  // z = M^-1 r, then r.z and r_prev.z in one pass (one all-reduce)
+    enqueue_vcycle(0, false, true);
+    for (auto& up : I.parts) {
+      PartDev& pd = *up;
+      LevelDev& l0 = *pd.lev[0];
+      I.set_dev(pd);
+      k_dot2<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(l0.b.p, l0.x.p, pd.rprev.p, (int)l0.n_own, pd.st.p, pd.partials.p, pd.rc);
+      I.note_launch("k_dot2");
+    }
+  } else if (precond) {
+    enqueue_vcycle(0, vcycle_fuses_rz(), true);
     if (!vcycle_fuses_rz()) enqueue_dot_rz();
   } else {
     for (auto& up : I.parts) {
@@ -1725,7 +1770,7 @@ void Engine::enqueue_pcg_iteration(bool precond) {
     PartDev& pd = *up;
     LevelDev& l0 = *pd.lev[0];
     I.set_dev(pd);
-    k_update_p<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.x.p, pd.p.p, (int)l0.n_own, pd.st.p, pd.rc);
+    k_update_p<<<I.grid_for(l0.n_own, BLOCK * 4), BLOCK, 0, pd.stream>>>(l0.x.p, pd.p.p, (int)l0.n_own, pd.st.p, pd.rc, flexible ? 1 : 0);
     I.note_launch("k_update_p");
   }
   {
@@ -1747,7 +1792,8 @@ void Engine::enqueue_pcg_iteration(bool precond) {
     k_update_xr<<<I.grid_red(l0.n_own), BLOCK, 0, pd.stream>>>(pd.xsol.p, l0.b.p, pd.p.p, pd.q.p, l0.xstart,
                                                                          zero_guess ? l0.w.p : nullptr, (int)l0.n_own, pd.st.p,
                                                                          pd.partials.p, pd.rc, I.fold_check ? 1 : 0, pd.hist.p,
-                                                                         up.get() == I.parts[0].get() ? I.hstat : nullptr);
+                                                                         up.get() == I.parts[0].get() ? I.hstat : nullptr,
+                                                                         flexible ? pd.rprev.p : nullptr);
     I.note_launch(I.fold_check ? "k_update_xr+check" : "k_update_xr");
   }
   if (!I.fold_check)  // several parts on one GPU: a kernel must not wait for a later kernel of its own stream
@@ -2007,7 +2053,7 @@ void Engine::enqueue_vcycle_entry() {
                                                                        (int)l0.n_own, pd.st.p);
       I.note_launch("k_scale");
     }
-  enqueue_vcycle(0, false);
+  enqueue_vcycle(0, false, true);
 }
 
 void Engine::vcycle(const double* const* b, double* const* x) {
@@ -2050,18 +2096,29 @@ void Engine::load_rhs(const double* const* b) {
 
 void Engine::read_solution(double* const* x) { download_vec(0, x, V_XSOL); }
 
-int Engine::pcg(const double* const* b, double* const* x, double rtol, int maxiter, bool precond, int* iters, double* hist) {
+int Engine::pcg(const double* const* b, double* const* x, double rtol, int maxiter, int mode, int* iters, double* hist) {
   load_rhs(b);
-  int rc = pcg_resident(rtol, maxiter, precond, iters, hist);
+  int rc = pcg_resident(rtol, maxiter, mode, iters, hist);
   read_solution(x);
   return rc;
 }
 
-int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, double* hist) {
+// mode: 0 plain CG, 1 AMG-preconditioned CG, 2 flexible AMG-preconditioned CG
+int Engine::pcg_resident(double rtol, int maxiter, int mode, int* iters, double* hist) {
   require_connected();
   Impl& I = *impl;
   if (!I.rhs_loaded) throw std::runtime_error("pamg_pcg_resident: call pamg_load_rhs first");
   if (maxiter < 0) throw std::runtime_error("maxiter < 0");
+  if (mode < 0 || mode > 2) throw std::runtime_error("bad Krylov mode");
+  const bool precond = mode != 0;
+  if (mode == 2)
+    for (auto& up : I.parts)
+      if (up->rprev.n == 0) {
+        I.set_dev(*up);
+        up->rprev.alloc((size_t)up->lev[0]->n_own);
+        for (auto g : I.g_iter) cudaGraphExecDestroy(g);
+        I.g_iter.clear();
+      }
   I.launches = 0;
   const bool use_graph = I.h->opts.use_graph != 0;
   for (auto& up : I.parts) {
@@ -2074,17 +2131,17 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
       I.g_iter.clear();
     }
   }
-  if (use_graph && (I.g_iter.empty() || I.g_iter_precond != precond)) {
+  if (use_graph && (I.g_iter.empty() || I.g_iter_mode != mode)) {
     I.names.clear();
     I.naming = true;
     try {
-      capture(I.g_iter, &I.g_iter_nodes, [&] { enqueue_pcg_iteration(precond); });
+      capture(I.g_iter, &I.g_iter_nodes, [&] { enqueue_pcg_iteration(mode); });
     } catch (...) {
       I.naming = false;
       throw;
     }
     I.naming = false;
-    I.g_iter_precond = precond;
+    I.g_iter_mode = mode;
   }
   const bool zero_guess = precond && I.L > 1 && I.h->opts.nu_pre > 0;
   sync_all();
@@ -2124,7 +2181,7 @@ int Engine::pcg_resident(double rtol, int maxiter, bool precond, int* iters, dou
           I.names.clear();
           I.naming = true;
         }
-        enqueue_pcg_iteration(precond);
+        enqueue_pcg_iteration(mode);
         I.naming = false;
       }
     }

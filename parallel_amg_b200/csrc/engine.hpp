@@ -47,9 +47,9 @@ class Engine {
   void prolong_correct(int level, const double* const* ec, double* const* x);
   double dot(int level, const double* const* u, const double* const* v);
   void vcycle(const double* const* b, double* const* x);
-  int pcg(const double* const* b, double* const* x, double rtol, int maxiter, bool precond, int* iters, double* hist);
+  int pcg(const double* const* b, double* const* x, double rtol, int maxiter, int mode, int* iters, double* hist);
   void load_rhs(const double* const* b);
-  int pcg_resident(double rtol, int maxiter, bool precond, int* iters, double* hist);
+  int pcg_resident(double rtol, int maxiter, int mode, int* iters, double* hist);
   void read_solution(double* const* x);
   void time_kernel(int kind, int level, int reps, bool flush_l2, float* ms_out);
   void get_stats(pamg_stats* s);
@@ -74,12 +74,12 @@ class Engine {
   void clear_done();
   void enqueue_op(const OpSpec& op, const std::vector<const double*>& xin, const std::vector<EpiArgs>& epi);
   void enqueue_smooth(int l, int nu, std::vector<double*>& cur, bool zero_guess_done, bool dot_last);
-  void enqueue_tail();
-  void enqueue_vcycle(int l, bool dot_rz);
+  void enqueue_tail(bool zero_guess);
+  void enqueue_vcycle(int l, bool dot_rz, bool zero_guess);
   void enqueue_vcycle_entry();
   void enqueue_dot_rz();
   bool vcycle_fuses_rz() const;
-  void enqueue_pcg_iteration(bool precond);
+  void enqueue_pcg_iteration(int mode);
   template <class F>
   void capture(std::vector<cudaGraphExec_t>& out, int64_t* nodes, F&& body);
   void launch_graphs(const std::vector<cudaGraphExec_t>& gs, int64_t nodes);

@@ -194,9 +194,12 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// one thread: wait until flags[0..n) have all reached epoch e.  Relaxed polls, then ONE system-scope fence supplies the
-// acquire for all of them (an ld.acquire.sys per flag costs a fence each: 8 parts => several us at the head of every
-// kernel that consumes an all-reduce or a halo).
+// one thread: wait until flags[0..n) have all reached epoch e.  The polls are relaxed system-scope loads; once every flag
+// is there ONE acquire load closes the wait (LDG.STRONG.SYS + an L1 invalidate).  Everything read behind a wait (ghost
+// staging, all-reduce slots, gather buffers) is read with ld.cv, i.e. at L2, and is only issued after the branch on the
+// flag value, so it cannot be older than the flag.  Measured alternatives: an ld.acquire.sys per flag serialises n L2
+// round trips at the head of every consumer (round 1); a __threadfence_system() after the polls is a MEMBAR.SC.SYS in each
+// of several hundred waiting CTAs while the main role streams -- +53 us per iteration on 2 GPUs (profiles/r02).
 __device__ __forceinline__ void spin_until_all(const uint32_t* flags, int n, uint32_t e, DevState* st) {
   unsigned long long t0 = 0;
   for (int k = 0; k < n; ++k) {
@@ -212,7 +215,7 @@ __device__ __forceinline__ void spin_until_all(const uint32_t* flags, int n, uin
       __nanosleep(32);
     }
   }
-  __threadfence_system();
+  if (n > 0) (void)ld_acquire_sys(flags);
 }
 
 // one thread: wait for every neighbour's flag of this level's current epoch; returns parity
@@ -1301,7 +1304,7 @@ __device__ __noinline__ void tail_stream_phase(const TailOp& op, double* prod) {
     stream_row_block<MODE, false, false>(op.A, op.x, op.a, nullptr, bk, prod, acc, bk + (int)gridDim.x < op.A.nblocks);
 }
 
-__global__ void __launch_bounds__(BLOCK, 2) k_tail_fused(const TailOp* __restrict__ ops, int n_ops, TailIO io, DevState* st) {
+__global__ void __launch_bounds__(BLOCK, 4) k_tail_fused(const TailOp* __restrict__ ops, int n_ops, TailIO io, DevState* st) {
   if (st->done) return;
   trace_mark(st);
   __shared__ double prod[S_STEPS * 4 * BLOCK];
@@ -1437,15 +1440,16 @@ __global__ void __launch_bounds__(BLOCK) k_pcg_init(const double* __restrict__ b
 }
 
 // beta = rz / rho_old ; p = z + beta p
+// flexible: beta = (r.z - r_prev.z) / rho_old  (Polak-Ribiere form of flexible CG; slots 1 and 3 of one all-reduce)
 __global__ void __launch_bounds__(BLOCK) k_update_p(const double* __restrict__ z, double* __restrict__ p, int n, DevState* st,
-                                                     RedCtx rc) {
+                                                     RedCtx rc, int flexible) {
   if (st->done) return;
   trace_mark(st);
   __shared__ double s_beta;
   if (threadIdx.x == 0) {
     double v[RED_W];
     red_consume(st, rc, v);
-    s_beta = v[1] / st->sc[SC_RHO_OLD];
+    s_beta = (flexible ? v[1] - v[3] : v[1]) / st->sc[SC_RHO_OLD];
     if (blockIdx.x == 0) st->sc[SC_RHO_NEW] = v[1];
   }
   __syncthreads();
@@ -1457,7 +1461,8 @@ __global__ void __launch_bounds__(BLOCK) k_update_p(const double* __restrict__ z
 __global__ void __launch_bounds__(BLOCK) k_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                                                       const double* __restrict__ q, double* __restrict__ z0,
                                                       const double* __restrict__ w, int n, DevState* st, double* partials,
-                                                      RedCtx rc, int fold_check, double* hist, HostStat* hs) {
+                                                      RedCtx rc, int fold_check, double* hist, HostStat* hs,
+                                                      double* __restrict__ rprev) {
   // fold_check (every part alone on its GPU): the block that publishes ||r||^2 also consumes the all-reduce and takes the
   // convergence decision, instead of a k_check launch behind this kernel
   if (st->done) {
@@ -1476,7 +1481,9 @@ __global__ void __launch_bounds__(BLOCK) k_update_xr(double* __restrict__ x, dou
   double acc = 0.0;
   for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
     x[i] += alpha * p[i];
-    const double ri = r[i] - alpha * q[i];
+    const double ro = r[i];
+    if (rprev) rprev[i] = ro;  // flexible CG keeps r_k for beta
+    const double ri = ro - alpha * q[i];
     r[i] = ri;
     z0[i] = w ? w[i] * ri : 0.0;
     acc += ri * ri;
@@ -1514,6 +1521,12 @@ __global__ void __launch_bounds__(BLOCK) k_copy_dot(const double* __restrict__ r
   dot_finish(acc, partials, st, &st->ticket[0], rc, 1, 0, 1);
 }
 
+__global__ void __launch_bounds__(BLOCK) k_copy(const double* __restrict__ src, double* __restrict__ dst, int n, DevState* st) {
+  if (st->done) return;
+  trace_mark(st);
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) dst[i] = src[i];
+}
+
 // out = w .* b  (zero-guess first Jacobi sweep) or out = 0 when w == nullptr
 __global__ void __launch_bounds__(BLOCK) k_scale(const double* __restrict__ b, const double* __restrict__ w, double* __restrict__ out,
                                                   int n, DevState* st) {
@@ -1530,6 +1543,37 @@ __global__ void __launch_bounds__(BLOCK) k_dot(const double* __restrict__ u, con
   double acc = 0.0;
   for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) acc += u[i] * v[i];
   dot_finish(acc, partials, st, &st->ticket[0], rc, 1, 0, slot);
+}
+// flexible CG: r.z (slot 1) and r_prev.z (slot 3) in one pass and one all-reduce
+__global__ void __launch_bounds__(BLOCK) k_dot2(const double* __restrict__ r, const double* __restrict__ z,
+                                                 const double* __restrict__ rprev, int n, DevState* st, double* partials, RedCtx rc) {
+  if (st->done) return;
+  trace_mark(st);
+  double a1 = 0.0, a3 = 0.0;
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+    const double zi = z[i];
+    a1 += r[i] * zi;
+    a3 += rprev[i] * zi;
+  }
+  const double b1 = block_sum(a1);
+  const double b3 = block_sum(a3);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = b1;
+    partials[gridDim.x + blockIdx.x] = b3;
+  }
+  if (last_block(&st->ticket[0])) {
+    double s1 = 0.0, s3 = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += BLOCK) {
+      s1 += __ldcv(partials + i);
+      s3 += __ldcv(partials + gridDim.x + i);
+    }
+    s1 = block_sum(s1);
+    s3 = block_sum(s3);
+    if (threadIdx.x == 0) {
+      double v[RED_W] = {0.0, s1, 0.0, s3};
+      red_publish(st, rc, v);
+    }
+  }
 }
 __global__ void k_red_read(DevState* st, RedCtx rc, double* out4) {
   double v[RED_W];

@@ -14,6 +14,8 @@ from util import det_vector, oracle_problem, own_of, own_parts, rel_err
     ((33, 31, 17), (3, 2, 1), {"nu_pre": 2, "nu_post": 2}),
     ((28, 28, 28), (1, 1, 1), {"smoother": "l1jacobi"}),
     ((7, 5), (1, 1), {}),
+    ((20, 20, 20), (2, 2, 1), {"cycle": "w", "coarse_size": 40}),
+    ((60, 60), (2, 2), {"cycle": "w", "coarse_size": 40, "nu_pre": 2, "nu_post": 1}),
 ])
 def test_c_oracle_matches_python_oracle(dims, pp, oopts):
     A, owner, h = oracle_problem(dims, pp, tuple(sorted(oopts.items())))
@@ -29,6 +31,9 @@ def test_c_oracle_matches_python_oracle(dims, pp, oopts):
         assert it == it_ref
         assert np.allclose(hist, hist_ref, rtol=1e-8)
         assert rel_err(x, own_of(lev, xs)) <= 1e-10
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, b), flexible=True)      # flexible CG (Polak-Ribiere beta)
+    x, it, hist = co.pcg(own_parts(lev, b), flexible=True)
+    assert it == it_ref and np.allclose(hist, hist_ref, rtol=1e-8) and rel_err(x, own_of(lev, xs)) <= 1e-10
     x, it, hist = co.pcg(own_parts(lev, b), precond=False, maxiter=400)
     xs, it_ref, _ = O.pcg(h, O.pvector_from_global(lev, b), precond=False, maxiter=400)
     assert it == it_ref

@@ -184,10 +184,13 @@ def test_pcg_iteration_count_and_history(dims, pp, oopts):
 
 @pytest.mark.parametrize("dims,pp", PROBLEMS[1:])
 @pytest.mark.parametrize("tail_rows", [0, 600, 1 << 20])
-def test_coarse_agglomeration_thresholds(dims, pp, tail_rows):
+@pytest.mark.parametrize("fused_tail", ["0", "1"], ids=["tail-launches", "tail-one-kernel"])
+def test_coarse_agglomeration_thresholds(dims, pp, tail_rows, fused_tail, monkeypatch):
     """Coarse-level agglomeration (levels merged over all parts and run replicated, pamg_options.tail_rows)
     is an execution layout, not a different hierarchy: whatever the threshold, the V-cycle matches the
-    oracle's N-part V-cycle to 1e-12 and PCG takes the same number of iterations."""
+    oracle's N-part V-cycle to 1e-12 and PCG takes the same number of iterations.  The tail runs either as one launch
+    per operation (default) or as ONE persistent kernel with grid barriers (PAMG_FUSED_TAIL=1): same row arithmetic."""
+    monkeypatch.setenv("PAMG_FUSED_TAIL", fused_tail)
     A, h, c = make(dims, pp, None, tail_rows=tail_rows)
     L_ = len(h["levels"])
     sizes = [h["global"]["levels"][l]["A"].shape[0] for l in range(L_)]
@@ -349,3 +352,55 @@ def test_product_setup_solves_config2_shape_and_is_symmetric_preconditioner():
     assert abs(v @ Mu - u @ Mv) <= 1e-10 * abs(v @ Mu)          # M symmetric (nu_pre == nu_post)
     Muv = c.vcycle([2.0 * u - 3.0 * v])[0]
     assert np.linalg.norm(Muv - (2.0 * Mu - 3.0 * Mv)) <= 1e-12 * np.linalg.norm(Muv)   # linear
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+@pytest.mark.parametrize("oopts", [{"cycle": "w", "coarse_size": 40}, {"cycle": "w", "coarse_size": 40, "nu_pre": 2, "nu_post": 1},
+                                   {"cycle": "w", "coarse_size": 40, "smoother": "chebyshev", "cheb_degree": 2}],
+                         ids=["w-jacobi11", "w-jacobi21", "w-cheb2"])
+def test_w_cycle_parity(dims, pp, oopts):
+    """W-cycle (pamg_options.cycle = PAMG_CYCLE_W): every coarse problem but the coarsest is visited twice, the second
+    visit continuing from the first one's result.  coarse_size 40 gives 4+ levels, so the recursion really nests."""
+    A, h, c = make(dims, pp, oopts)
+    assert len(h["levels"]) >= 3
+    lev = h["levels"][0]
+    n = A.shape[0]
+    b = det_vector(n, 73)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    hv = dict(h)
+    hv["opts"] = dict(h["opts"], cycle="v")
+    assert rel_err(own_of(lev, O.vcycle(hv, O.pvector_from_global(lev, b))), ref) > 1e-6   # it is not a V-cycle in disguise
+    rhs = A @ det_vector(n, 74)
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, rhs))
+    x, it, hist, ok = c.pcg(own_parts(lev, rhs))
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
+
+
+@pytest.mark.parametrize("tail_rows", [0, 600, 1 << 20])
+def test_w_cycle_with_agglomerated_tail(tail_rows):
+    oopts = {"cycle": "w", "coarse_size": 40}
+    A, h, c = make((20, 20, 20), (2, 2, 2), oopts, tail_rows=tail_rows)
+    lev = h["levels"][0]
+    b = det_vector(A.shape[0], 75)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+@pytest.mark.parametrize("oopts", [{}, {"cycle": "w", "coarse_size": 40}], ids=["v", "w"])
+def test_flexible_cg_parity(dims, pp, oopts):
+    """pamg_fcg: flexible (Polak-Ribiere) AMG-preconditioned CG against the oracle's pcg(flexible=True)."""
+    A, h, c = make(dims, pp, oopts)
+    lev = h["levels"][0]
+    n = A.shape[0]
+    rhs = A @ det_vector(n, 83)
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, rhs), flexible=True)
+    for rep in range(2):
+        x, it, hist, ok = c.fcg(own_parts(lev, rhs))
+        assert ok and it == it_ref
+        assert np.allclose(hist, hist_ref, rtol=1e-7)
+        assert rel_err(x, own_of(lev, xs)) <= 1e-10
+    x2, it2, hist2, ok2 = c.pcg(own_parts(lev, rhs))     # switching drivers on one context re-captures the iteration graph
+    xs2, it_ref2, hist_ref2 = O.pcg(h, O.pvector_from_global(lev, rhs))
+    assert ok2 and it2 == it_ref2 and np.allclose(hist2, hist_ref2, rtol=1e-7)

@@ -14,6 +14,8 @@ def product_options(ctx, oopts, **extra):
     for k, v in (oopts or {}).items():
         if k == "smoother":
             kw[k] = SMOOTHERS[v]
+        elif k == "cycle":
+            kw[k] = {"v": L.CYCLE_V, "w": L.CYCLE_W}[v]
         else:
             kw[k] = v
     kw.update(extra)
