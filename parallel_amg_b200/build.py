@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libpamg.so")
 STAMP = os.path.join(HERE, ".libpamg.stamp")
 
 CXX_SOURCES = ["host_setup.cpp", "hierarchy_io.cpp", "capi.cpp"]
-CU_SOURCES = ["engine.cu"]
+CU_SOURCES = ["engine.cu", "setup_gpu.cu"]
 DEPS = ["host.hpp", "engine.hpp", "formats.hpp", "kernels.cuh", os.path.join("..", "..", "include", "pamg.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -481,7 +481,8 @@ struct Engine::Impl {
   bool fused_tail = false;  // replicated tail as ONE persistent kernel (env PAMG_FUSED_TAIL=1; measured slower than one launch per operation)
   int tail_ctas = 2 * 148;  // its grid (env PAMG_TAIL_CTAS), capped by the occupancy limit: all CTAs must be resident
   std::vector<std::vector<TailOp>>* tail_rec = nullptr;  // != nullptr: enqueue_* record tail phases instead of launching
-  int unified = 15;         // fused persistent SELL launches run without role CTAs: bit mask over operator classes (env PAMG_UNIFIED)
+  int unified = 0;          // fused persistent SELL launches without role CTAs: bit mask over operator classes (env PAMG_UNIFIED;
+                            // 1 A short rows, 2 A long rows, 4 P, 8 R).  Off: measured +67 us per iteration on 8 GPUs (profiles/r02)
   bool fold_check = false;  // the convergence check runs inside k_update_xr / k_pcg_init (every local part alone on its GPU)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;

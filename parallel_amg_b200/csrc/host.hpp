@@ -76,6 +76,12 @@ void gallery_poisson(int ndim, const int64_t* dims, Csr& A);
 void gallery_diffusion_jump(int ndim, const int64_t* dims, int blocks, double kmax, double eps_z, Csr& A);
 void matvec(const Csr& A, const double* x, double* y);
 
+// ---- sparse products of the setup on the GPU (setup_gpu.cu) ----------------------------------
+// gpu_setup_available: a CUDA device is present and PAMG_GPU_SETUP != 0.  gpu_spgemm: C = A*B with the host product's
+// accumulation order (bit-identical structure and values); throws on CUDA errors (the caller falls back to the host).
+bool gpu_setup_available();
+void gpu_spgemm(const Csr& A, const Csr& B, Csr& C);
+
 // ---- setup ------------------------------------------------------------------------------------
 // Builds every level (global matrices internally, then the per-part split format).
 // Throws std::runtime_error on bad input; the C ABI catches.

@@ -354,6 +354,19 @@ static void spgemm(const Csr& A, const Csr& B, Csr& C) {
   }
 }
 
+// C = A*B on the GPU when one is there (same accumulation order, same bits), else on the host cores
+static void product(const Csr& A, const Csr& B, Csr& C, bool gpu) {
+  if (gpu) {
+    try {
+      gpu_spgemm(A, B, C);
+      return;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "[pamg setup] GPU product failed (%s): falling back to the host\n", e.what());
+    }
+  }
+  spgemm(A, B, C);
+}
+
 static void transpose(const Csr& A, Csr& T) {
   T.nrows = A.ncols;
   T.ncols = A.nrows;
@@ -472,7 +485,7 @@ static int64_t aggregate_part(const Csr& A, const std::vector<int32_t>& owner, c
 // P0: tentative prolongator (n x nc, sorted columns): one unit entry per row for scalar problems, the
 // per-aggregate Q factors of the near-nullspace for block problems.
 static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double eps,
-                              const std::vector<double>& absdiag, Csr& P, double* omega_out) {
+                              const std::vector<double>& absdiag, Csr& P, double* omega_out, bool gpu) {
   const int64_t n = A.nrows;
   // filtered matrix A_F (weak off-diagonals lumped into the diagonal); eps == 0 => A_F = A
   Csr AF;
@@ -532,64 +545,50 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
   const double omega = 4.0 / (3.0 * rho);
   *omega_out = omega;
 
+  // S = A_F P0 (structural product, encounter-order sums), then P = P0 - omega D_F^-1 S merged by column
+  Csr S;
+  product(*F, P0, S, gpu);
   P.nrows = n;
   P.ncols = nc;
   P.ptr.assign(n + 1, 0);
-  const int nt = omp_get_max_threads();
-  std::vector<std::vector<int64_t>> tcol(nt);
-  std::vector<std::vector<double>> tval(nt);
-#pragma omp parallel num_threads(nt)
-  {
-    const int t = omp_get_thread_num();
-    const int64_t r0 = n * t / nt, r1 = n * (t + 1) / nt;
-    RowAccumulator acc(nc);
-    for (int64_t i = r0; i < r1; ++i) {
-      acc.clear();
-      for (int64_t k = F->ptr[i]; k < F->ptr[i + 1]; ++k) {
-        const int64_t j = F->col[k];
-        const double f = F->val[k];
-        for (int64_t kb = P0.ptr[j]; kb < P0.ptr[j + 1]; ++kb) acc.add(P0.col[kb], f * P0.val[kb]);
-      }
-      const double w = -(omega * dinv[i]);
-      int64_t pk = P0.ptr[i];  // next tentative entry of this row still to be placed
-      const int64_t pe = P0.ptr[i + 1];
-      int64_t cnt = 0;
-      for (int32_t q : acc.sorted()) {
-        const int64_t c = acc.cols[q];
-        const double s = acc.vals[q];
-        while (pk < pe && P0.col[pk] < c) {  // tentative entries without an A_F P0 partner
-          tcol[t].push_back(P0.col[pk]);
-          tval[t].push_back(P0.val[pk]);
-          ++pk;
-          ++cnt;
-        }
-        double v = w * s;
-        if (pk < pe && P0.col[pk] == c) {
-          v = P0.val[pk] + v;
-          ++pk;
-        }
-        tcol[t].push_back(c);
-        tval[t].push_back(v);
-        ++cnt;
-      }
-      while (pk < pe) {
-        tcol[t].push_back(P0.col[pk]);
-        tval[t].push_back(P0.val[pk]);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t pk = P0.ptr[i], cnt = 0;
+    const int64_t pe = P0.ptr[i + 1];
+    for (int64_t k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const int64_t c = S.col[k];
+      while (pk < pe && P0.col[pk] < c) {  // tentative entries without an A_F P0 partner
         ++pk;
         ++cnt;
       }
-      P.ptr[i + 1] = cnt;
+      if (pk < pe && P0.col[pk] == c) ++pk;
+      ++cnt;
     }
+    P.ptr[i + 1] = cnt + (pe - pk);
   }
   for (int64_t i = 0; i < n; ++i) P.ptr[i + 1] += P.ptr[i];
   P.col.resize(P.ptr[n]);
   P.val.resize(P.ptr[n]);
-#pragma omp parallel num_threads(nt)
-  {
-    const int t = omp_get_thread_num();
-    const int64_t r0 = n * t / nt;
-    std::copy(tcol[t].begin(), tcol[t].end(), P.col.begin() + P.ptr[r0]);
-    std::copy(tval[t].begin(), tval[t].end(), P.val.begin() + P.ptr[r0]);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const double w = -(omega * dinv[i]);
+    int64_t pk = P0.ptr[i], q = P.ptr[i];
+    const int64_t pe = P0.ptr[i + 1];
+    for (int64_t k = S.ptr[i]; k < S.ptr[i + 1]; ++k) {
+      const int64_t c = S.col[k];
+      while (pk < pe && P0.col[pk] < c) {
+        P.col[q] = P0.col[pk];
+        P.val[q++] = P0.val[pk++];
+      }
+      double v = w * S.val[k];
+      if (pk < pe && P0.col[pk] == c) v = P0.val[pk++] + v;
+      P.col[q] = c;
+      P.val[q++] = v;
+    }
+    while (pk < pe) {
+      P.col[q] = P0.col[pk];
+      P.val[q++] = P0.val[pk++];
+    }
   }
 }
 
@@ -914,6 +913,8 @@ struct PhaseTimer {  // PAMG_SETUP_TIMING=1: per-phase wall time of the host set
 void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t nparts, const pamg_options& o, Hierarchy& h,
                      int32_t block_size, int32_t ns_k, const std::vector<double>* nullspace) {
   PhaseTimer tm;
+  const bool gpu = gpu_setup_available();  // the three sparse products of every level run on the GPU when one is there
+  if (tm.on) std::fprintf(stderr, "[pamg setup] sparse products on the %s\n", gpu ? "GPU" : "host");
   if (A0.nrows != (int64_t)owner0.size()) throw std::runtime_error("owner size mismatch");
   const bool use_ns = nullspace && ns_k > 0;
   if (block_size < 1) block_size = 1;
@@ -1019,16 +1020,16 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       tentative_from_nullspace(Bcur, kdof, bs, agg_node, nagg, P0, Bc, dead);
     }
     tm.lap("aggregation + P0", (int)g.size() - 1);
-    build_prolongator(cur.A, P0, nc, eps, absdiag, cur.P, &cur.omega_p);
+    build_prolongator(cur.A, P0, nc, eps, absdiag, cur.P, &cur.omega_p, gpu);
     tm.lap("prolongator smoothing", (int)g.size() - 1);
     transpose(cur.P, cur.R);
     tm.lap("transpose", (int)g.size() - 1);
     G nxt;
     {
       Csr AP;
-      spgemm(cur.A, cur.P, AP);
+      product(cur.A, cur.P, AP, gpu);
       tm.lap("A*P", (int)g.size() - 1);
-      spgemm(cur.R, AP, nxt.A);
+      product(cur.R, AP, nxt.A, gpu);
       tm.lap("R*(AP)", (int)g.size() - 1);
     }
     for (int64_t gd : dead) {  // empty coarse column: unit diagonal keeps the Galerkin matrix regular
