@@ -1550,7 +1550,12 @@ void Engine::enqueue_tail(bool zero_guess) {
       io.inv = pd.inv.p;
       io.do_gather = fold_gather ? 1 : 0;
       const int grid = std::max(1, std::min(I.tail_ctas, resident_ctas((const void*)k_tail_fused)));
-      k_tail_fused<<<grid, BLOCK, 0, pd.stream>>>(pd.tail_ops.p, pd.n_tail_ops, io, pd.st.p);
+      // cooperative launch: the grid barrier needs every CTA resident, and the runtime refuses the launch otherwise
+      const TailOp* ops_arg = pd.tail_ops.p;
+      int n_ops_arg = pd.n_tail_ops;
+      DevState* st_arg = pd.st.p;
+      void* args[] = {(void*)&ops_arg, (void*)&n_ops_arg, (void*)&io, (void*)&st_arg};
+      CK(cudaLaunchCooperativeKernel((const void*)k_tail_fused, dim3(grid), dim3(BLOCK), args, 0, pd.stream));
       I.note_launch(fold_gather ? "k_tail_fused (gather + tail V-cycle + scatter)" : "k_tail_fused (tail V-cycle + scatter)");
     }
     CK(cudaGetLastError());

@@ -81,6 +81,13 @@ void matvec(const Csr& A, const double* x, double* y);
 // accumulation order (bit-identical structure and values); throws on CUDA errors (the caller falls back to the host).
 bool gpu_setup_available();
 void gpu_spgemm(const Csr& A, const Csr& B, Csr& C);
+// the same with device-resident operands, so that a chain of products (A_F*P0, A*P, R*(A*P), the next level's A) pays the
+// PCIe transfer of every matrix at most once
+struct GpuMat;
+GpuMat* gpu_upload(const Csr& A);
+GpuMat* gpu_product(const GpuMat* A, const GpuMat* B);
+void gpu_download(const GpuMat* m, Csr& C);
+void gpu_free(GpuMat* m);
 
 // ---- setup ------------------------------------------------------------------------------------
 // Builds every level (global matrices internally, then the per-part split format).

@@ -367,21 +367,51 @@ static void product(const Csr& A, const Csr& B, Csr& C, bool gpu) {
   spgemm(A, B, C);
 }
 
+// T = A^T with ascending columns in every row.  Parallel counting sort: the threads own contiguous row ranges of A, the
+// per-thread column counts are turned into per-thread write offsets, so that inside a row of T the entries of a lower
+// thread (= lower row ids of A) come first and every thread appends in ascending row order: deterministic and sorted.
 static void transpose(const Csr& A, Csr& T) {
   T.nrows = A.ncols;
   T.ncols = A.nrows;
-  T.ptr.assign(T.nrows + 1, 0);
-  for (int64_t k = 0; k < A.nnz(); ++k) T.ptr[A.col[k] + 1]++;
-  for (int64_t i = 0; i < T.nrows; ++i) T.ptr[i + 1] += T.ptr[i];
+  const int64_t nc = A.ncols, nr = A.nrows;
+  T.ptr.assign(nc + 1, 0);
   T.col.resize(A.nnz());
   T.val.resize(A.nnz());
-  std::vector<int64_t> pos(T.ptr.begin(), T.ptr.end() - 1);
-  for (int64_t i = 0; i < A.nrows; ++i)
-    for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
-      int64_t q = pos[A.col[k]]++;
-      T.col[q] = i;
-      T.val[q] = A.val[k];
+  int nt = omp_get_max_threads();
+  // per-thread count arrays cost nt * ncols words: fall back to fewer threads for very wide matrices
+  while (nt > 1 && (int64_t)nt * nc > ((int64_t)1 << 28)) nt /= 2;
+  std::vector<std::vector<int64_t>> cnt(nt);
+#pragma omp parallel num_threads(nt)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t r0 = nr * t / nt, r1 = nr * (t + 1) / nt;
+    cnt[t].assign(nc, 0);
+    for (int64_t k = A.ptr[r0]; k < A.ptr[r1]; ++k) cnt[t][A.col[k]]++;
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < nc; ++c) {
+    int64_t s = 0;
+    for (int t = 0; t < nt; ++t) {
+      const int64_t v = cnt[t][c];
+      cnt[t][c] = s;  // offset of thread t inside row c of T
+      s += v;
     }
+    T.ptr[c + 1] = s;
+  }
+  for (int64_t c = 0; c < nc; ++c) T.ptr[c + 1] += T.ptr[c];
+#pragma omp parallel num_threads(nt)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t r0 = nr * t / nt, r1 = nr * (t + 1) / nt;
+    std::vector<int64_t>& off = cnt[t];
+    for (int64_t i = r0; i < r1; ++i)
+      for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+        const int64_t c = A.col[k];
+        const int64_t q = T.ptr[c] + off[c]++;
+        T.col[q] = i;
+        T.val[q] = A.val[k];
+      }
+  }
 }
 
 static void diagonal(const Csr& A, std::vector<double>& d) {
@@ -416,17 +446,43 @@ static void build_own_index(const std::vector<int32_t>& owner, int32_t nparts, O
   const int64_t n = (int64_t)owner.size();
   oi.own.assign(nparts, {});
   oi.lid.resize(n);
-  std::vector<int64_t> cnt(nparts, 0);
-  for (int64_t g = 0; g < n; ++g) {
-    if (owner[g] < 0 || owner[g] >= nparts) throw std::runtime_error("owner id out of range");
-    cnt[owner[g]]++;
+  const int nt = omp_get_max_threads();
+  std::vector<std::vector<int64_t>> cnt(nt, std::vector<int64_t>(nparts, 0));
+  bool bad = false;
+#pragma omp parallel num_threads(nt)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t g0 = n * t / nt, g1 = n * (t + 1) / nt;
+    for (int64_t g = g0; g < g1; ++g) {
+      if (owner[g] < 0 || owner[g] >= nparts) {
+#pragma omp atomic write
+        bad = true;
+        continue;
+      }
+      cnt[t][owner[g]]++;
+    }
   }
-  for (int32_t p = 0; p < nparts; ++p) oi.own[p].reserve(cnt[p]);
-  for (int64_t g = 0; g < n; ++g) {
-    auto& v = oi.own[owner[g]];
-    if ((int64_t)v.size() >= INT32_MAX) throw std::runtime_error("part too large for int32 local ids");
-    oi.lid[g] = (int32_t)v.size();
-    v.push_back(g);
+  if (bad) throw std::runtime_error("owner id out of range");
+  for (int32_t p = 0; p < nparts; ++p) {  // counts -> first position of thread t inside part p's own list
+    int64_t s = 0;
+    for (int t = 0; t < nt; ++t) {
+      const int64_t v = cnt[t][p];
+      cnt[t][p] = s;
+      s += v;
+    }
+    if (s >= INT32_MAX) throw std::runtime_error("part too large for int32 local ids");
+    oi.own[p].resize(s);
+  }
+#pragma omp parallel num_threads(nt)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t g0 = n * t / nt, g1 = n * (t + 1) / nt;
+    std::vector<int64_t>& pos = cnt[t];
+    for (int64_t g = g0; g < g1; ++g) {  // ascending gid inside every part, as before
+      const int64_t q = pos[owner[g]]++;
+      oi.lid[g] = (int32_t)q;
+      oi.own[owner[g]][q] = g;
+    }
   }
 }
 
@@ -484,8 +540,9 @@ static int64_t aggregate_part(const Csr& A, const std::vector<int32_t>& owner, c
 // ------------------------------------------------------------------------------------------
 // P0: tentative prolongator (n x nc, sorted columns): one unit entry per row for scalar problems, the
 // per-aggregate Q factors of the near-nullspace for block problems.
+// dA: the device copy of A when the GPU chain is on (used for S = A P0 when no filtering makes A_F = A), else nullptr
 static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double eps,
-                              const std::vector<double>& absdiag, Csr& P, double* omega_out, bool gpu) {
+                              const std::vector<double>& absdiag, Csr& P, double* omega_out, bool gpu, const GpuMat* dA) {
   const int64_t n = A.nrows;
   // filtered matrix A_F (weak off-diagonals lumped into the diagonal); eps == 0 => A_F = A
   Csr AF;
@@ -547,7 +604,21 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
 
   // S = A_F P0 (structural product, encounter-order sums), then P = P0 - omega D_F^-1 S merged by column
   Csr S;
-  product(*F, P0, S, gpu);
+  bool done = false;
+  if (gpu && dA && F == &A) {  // A is already resident: upload only P0, download only S
+    GpuMat *dP0 = nullptr, *dS = nullptr;
+    try {
+      dP0 = gpu_upload(P0);
+      dS = gpu_product(dA, dP0);
+      gpu_download(dS, S);
+      done = true;
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "[pamg setup] GPU product failed (%s): falling back to the host\n", e.what());
+    }
+    gpu_free(dP0);
+    gpu_free(dS);
+  }
+  if (!done) product(*F, P0, S, gpu);
   P.nrows = n;
   P.ncols = nc;
   P.ptr.assign(n + 1, 0);
@@ -787,9 +858,23 @@ static void index_maps(const Csr& A, const std::vector<int32_t>& owner, const Ow
   pl.own_to_global = oi.own[p];
   pl.n_own = (int64_t)pl.own_to_global.size();
   std::vector<std::pair<int32_t, int64_t>> gh;
-  for (int64_t i : pl.own_to_global)
-    for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k)
-      if (owner[A.col[k]] != p) gh.emplace_back(owner[A.col[k]], A.col[k]);
+  {  // (inside a parallel loop over parts this region is serialised; with fewer parts than threads it is the parallel one)
+    const int64_t no = pl.n_own;
+#pragma omp parallel
+    {
+      std::vector<std::pair<int32_t, int64_t>> loc;
+#pragma omp for schedule(static) nowait
+      for (int64_t r = 0; r < no; ++r) {
+        const int64_t i = pl.own_to_global[r];
+        for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k)
+          if (owner[A.col[k]] != p) loc.emplace_back(owner[A.col[k]], A.col[k]);
+      }
+      std::sort(loc.begin(), loc.end());
+      loc.erase(std::unique(loc.begin(), loc.end()), loc.end());
+#pragma omp critical(pamg_index_maps)
+      gh.insert(gh.end(), loc.begin(), loc.end());
+    }
+  }
   std::sort(gh.begin(), gh.end());
   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
   pl.n_ghost = (int64_t)gh.size();
@@ -811,41 +896,56 @@ static void split_blocks(const Csr& M, const std::vector<int64_t>& rows, const s
   og.ncols = n_ghost_c;
   oo.ptr.assign(nr + 1, 0);
   og.ptr.assign(nr + 1, 0);
+#pragma omp parallel for schedule(static)
   for (int64_t r = 0; r < nr; ++r) {
     const int64_t i = rows[r];
     int64_t a = 0, b = 0;
     for (int64_t k = M.ptr[i]; k < M.ptr[i + 1]; ++k) (owner_c[M.col[k]] == p ? a : b)++;
-    oo.ptr[r + 1] = oo.ptr[r] + a;
-    og.ptr[r + 1] = og.ptr[r] + b;
+    oo.ptr[r + 1] = a;
+    og.ptr[r + 1] = b;
+  }
+  for (int64_t r = 0; r < nr; ++r) {
+    oo.ptr[r + 1] += oo.ptr[r];
+    og.ptr[r + 1] += og.ptr[r];
   }
   if (oo.ptr[nr] > INT32_MAX || og.ptr[nr] > INT32_MAX) throw std::runtime_error("block nnz exceeds int32");
   oo.col.resize(oo.ptr[nr]);
   oo.val.resize(oo.ptr[nr]);
   og.col.resize(og.ptr[nr]);
   og.val.resize(og.ptr[nr]);
-  std::vector<std::pair<int32_t, double>> tmp;
-  for (int64_t r = 0; r < nr; ++r) {
-    const int64_t i = rows[r];
-    int64_t qa = oo.ptr[r];
-    tmp.clear();
-    for (int64_t k = M.ptr[i]; k < M.ptr[i + 1]; ++k) {
-      const int64_t j = M.col[k];
-      if (owner_c[j] == p) {
-        oo.col[qa] = lid_c[j];
-        oo.val[qa++] = M.val[k];
-      } else {
-        const int32_t s = gl.find(j);
-        if (s < 0) throw std::runtime_error("column outside the part's own+ghost set");
-        tmp.emplace_back(s, M.val[k]);
+  bool missing = false;
+#pragma omp parallel
+  {
+    std::vector<std::pair<int32_t, double>> tmp;
+#pragma omp for schedule(static)
+    for (int64_t r = 0; r < nr; ++r) {
+      const int64_t i = rows[r];
+      int64_t qa = oo.ptr[r];
+      tmp.clear();
+      for (int64_t k = M.ptr[i]; k < M.ptr[i + 1]; ++k) {
+        const int64_t j = M.col[k];
+        if (owner_c[j] == p) {
+          oo.col[qa] = lid_c[j];
+          oo.val[qa++] = M.val[k];
+        } else {
+          const int32_t sl = gl.find(j);
+          if (sl < 0) {
+#pragma omp atomic write
+            missing = true;
+            continue;
+          }
+          tmp.emplace_back(sl, M.val[k]);
+        }
+      }
+      std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y) { return x.first < y.first; });
+      int64_t qb = og.ptr[r];
+      for (auto& e : tmp) {
+        og.col[qb] = e.first;
+        og.val[qb++] = e.second;
       }
     }
-    std::sort(tmp.begin(), tmp.end(), [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y) { return x.first < y.first; });
-    int64_t qb = og.ptr[r];
-    for (auto& e : tmp) {
-      og.col[qb] = e.first;
-      og.val[qb++] = e.second;
-    }
   }
+  if (missing) throw std::runtime_error("column outside the part's own+ghost set");
 }
 
 void build_halo_plans(Level& lev, int32_t nparts) {
@@ -883,6 +983,8 @@ static void fill_diag(PartLevel& pl) {
   const LocalCsr& og = pl.blk[PAMG_A_OG];
   pl.diag.assign(pl.n_own, 0.0);
   pl.diag_l1.assign(pl.n_own, 0.0);
+  bool zero = false;
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < pl.n_own; ++i) {
     for (int64_t k = oo.ptr[i]; k < oo.ptr[i + 1]; ++k)
       if (oo.col[k] == i) pl.diag[i] = oo.val[k];
@@ -890,8 +992,12 @@ static void fill_diag(PartLevel& pl) {
     if (!og.ptr.empty())
       for (int64_t k = og.ptr[i]; k < og.ptr[i + 1]; ++k) s += std::fabs(og.val[k]);
     pl.diag_l1[i] = pl.diag[i] + s;
-    if (pl.diag[i] == 0.0) throw std::runtime_error("zero diagonal");
+    if (pl.diag[i] == 0.0) {
+#pragma omp atomic write
+      zero = true;
+    }
   }
+  if (zero) throw std::runtime_error("zero diagonal");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -913,7 +1019,12 @@ struct PhaseTimer {  // PAMG_SETUP_TIMING=1: per-phase wall time of the host set
 void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t nparts, const pamg_options& o, Hierarchy& h,
                      int32_t block_size, int32_t ns_k, const std::vector<double>* nullspace) {
   PhaseTimer tm;
-  const bool gpu = gpu_setup_available();  // the three sparse products of every level run on the GPU when one is there
+  bool gpu = gpu_setup_available();  // the three sparse products of every level run on the GPU when one is there
+  GpuMat* dA = nullptr;              // device copy of the current level's matrix (GPU chain)
+  struct DaGuard {                   // an exception below must not leak device memory
+    GpuMat*& p;
+    ~DaGuard() { gpu_free(p); }
+  } da_guard{dA};
   if (tm.on) std::fprintf(stderr, "[pamg setup] sparse products on the %s\n", gpu ? "GPU" : "host");
   if (A0.nrows != (int64_t)owner0.size()) throw std::runtime_error("owner size mismatch");
   const bool use_ns = nullspace && ns_k > 0;
@@ -929,28 +1040,46 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
   h.opts = o;
 
   struct G {
-    Csr A, P, R;
+    Csr A_own, P, R;        // A_own: the Galerkin matrix of a coarse level (level 0 borrows the caller's matrix: no 2 GB copy)
+    const Csr* Ap = nullptr;
+    const Csr& A() const { return *Ap; }
     std::vector<int32_t> owner;
     OwnIndex oi;
     std::vector<int32_t> agg_loc;  // by gid
     double rho = 0, omega_p = 0;
   };
   std::vector<G> g(1);
-  g[0].A = A0;
+  g.reserve((size_t)std::max(o.max_levels, 1) + 1);  // no reallocation: G::Ap points into the elements
+  g[0].Ap = &A0;
   g[0].owner = owner0;
   while (true) {
     const double eps = o.eps_strength * std::pow(0.5, (double)(g.size() - 1));  // Vanek: eps_l = eps 2^-l
     G& cur = g.back();
-    const int64_t n = cur.A.nrows;
+    const int64_t n = cur.A().nrows;
+    if (gpu && !dA && n > o.coarse_size && (int32_t)g.size() < o.max_levels) {
+      try {
+        dA = gpu_upload(cur.A());
+      } catch (const std::exception& e) {
+        std::fprintf(stderr, "[pamg setup] GPU upload failed (%s): sparse products on the host\n", e.what());
+        gpu = false;
+      }
+    }
     build_own_index(cur.owner, nparts, cur.oi);
     std::vector<double> d, dinv(n), absdiag(n);
-    diagonal(cur.A, d);
+    diagonal(cur.A(), d);
+    bool zero_diag = false;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
-      if (d[i] == 0.0) throw std::runtime_error("zero diagonal");
+      if (d[i] == 0.0) {
+#pragma omp atomic write
+        zero_diag = true;
+        continue;
+      }
       dinv[i] = 1.0 / d[i];
       absdiag[i] = std::fabs(d[i]);
     }
-    cur.rho = gershgorin_rho(cur.A, dinv);
+    if (zero_diag) throw std::runtime_error("zero diagonal");
+    cur.rho = gershgorin_rho(cur.A(), dinv);
     tm.lap("own index + diagonal", (int)g.size() - 1);
     if (n <= o.coarse_size || (int32_t)g.size() >= o.max_levels) break;
 
@@ -967,7 +1096,7 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       OmpGuard og;
 #pragma omp parallel for schedule(dynamic, 1)
       for (int32_t p = 0; p < nparts; ++p)
-        og.run([&] { counts[p] = aggregate_part(cur.A, cur.owner, cur.oi, p, eps, absdiag, aggs[p]); });
+        og.run([&] { counts[p] = aggregate_part(cur.A(), cur.owner, cur.oi, p, eps, absdiag, aggs[p]); });
       og.rethrow();
       for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
       nc = off[nparts];
@@ -997,7 +1126,7 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
           if (cur.owner[v * bs + d] != owner_node[v]) throw std::runtime_error("the DOFs of a node must share one owner");
       }
       Csr N;
-      node_graph(cur.A, bs, N);
+      node_graph(cur.A(), bs, N);
       OwnIndex oin;
       build_own_index(owner_node, nparts, oin);
       std::vector<double> none;
@@ -1020,31 +1149,61 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       tentative_from_nullspace(Bcur, kdof, bs, agg_node, nagg, P0, Bc, dead);
     }
     tm.lap("aggregation + P0", (int)g.size() - 1);
-    build_prolongator(cur.A, P0, nc, eps, absdiag, cur.P, &cur.omega_p, gpu);
+    build_prolongator(cur.A(), P0, nc, eps, absdiag, cur.P, &cur.omega_p, gpu, dA);
     tm.lap("prolongator smoothing", (int)g.size() - 1);
     transpose(cur.P, cur.R);
     tm.lap("transpose", (int)g.size() - 1);
     G nxt;
-    {
+    bool galerkin_done = false;
+    GpuMat* dAc = nullptr;
+    if (gpu && dA) {  // A is resident: A*P stays on the device, only P, R go up and A_c comes down
+      GpuMat *dP = nullptr, *dR = nullptr, *dAP = nullptr;
+      try {
+        dP = gpu_upload(cur.P);
+        dAP = gpu_product(dA, dP);
+        tm.lap("A*P (GPU)", (int)g.size() - 1);
+        dR = gpu_upload(cur.R);
+        dAc = gpu_product(dR, dAP);
+        gpu_download(dAc, nxt.A_own);
+        tm.lap("R*(AP) (GPU)", (int)g.size() - 1);
+        galerkin_done = true;
+      } catch (const std::exception& e) {
+        std::fprintf(stderr, "[pamg setup] GPU Galerkin product failed (%s): falling back to the host\n", e.what());
+        gpu_free(dAc);
+        dAc = nullptr;
+      }
+      gpu_free(dP);
+      gpu_free(dR);
+      gpu_free(dAP);
+    }
+    gpu_free(dA);  // the fine matrix is not needed on the device any more
+    dA = nullptr;
+    if (!galerkin_done) {
       Csr AP;
-      product(cur.A, cur.P, AP, gpu);
+      product(cur.A(), cur.P, AP, gpu);
       tm.lap("A*P", (int)g.size() - 1);
-      product(cur.R, AP, nxt.A, gpu);
+      product(cur.R, AP, nxt.A_own, gpu);
       tm.lap("R*(AP)", (int)g.size() - 1);
     }
     for (int64_t gd : dead) {  // empty coarse column: unit diagonal keeps the Galerkin matrix regular
       bool found = false;
-      for (int64_t k = nxt.A.ptr[gd]; k < nxt.A.ptr[gd + 1]; ++k)
-        if (nxt.A.col[k] == gd) {
-          nxt.A.val[k] = 1.0;
+      for (int64_t k = nxt.A_own.ptr[gd]; k < nxt.A_own.ptr[gd + 1]; ++k)
+        if (nxt.A_own.col[k] == gd) {
+          nxt.A_own.val[k] = 1.0;
           found = true;
         }
       if (!found) throw std::runtime_error("internal: no diagonal slot for an empty coarse column");
     }
+    if (!dead.empty() && dAc) {  // the host copy was edited: the device copy is stale
+      gpu_free(dAc);
+      dAc = nullptr;
+    }
+    dA = dAc;  // next level's A, already on the device (or nullptr: uploaded at the top of the loop)
     nxt.owner.resize(nc);
     for (int32_t p = 0; p < nparts; ++p)
       for (int64_t c = off[p] * kdof; c < off[p + 1] * kdof; ++c) nxt.owner[c] = p;
     g.push_back(std::move(nxt));
+    g.back().Ap = &g.back().A_own;
     if (use_ns) {
       Bcur.swap(Bc);
       bs = kdof;
@@ -1057,15 +1216,16 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
   std::vector<std::vector<GhostLookup>> gl(L, std::vector<GhostLookup>(nparts));
   for (int32_t l = 0; l < L; ++l) {
     Level& lev = h.levels[l];
-    lev.n_global = g[l].A.nrows;
+    lev.n_global = g[l].A().nrows;
     lev.rho = g[l].rho;
     lev.omega_p = g[l].omega_p;
     lev.parts.resize(nparts);
     OmpGuard og;
-#pragma omp parallel for schedule(dynamic, 1)
+    // few parts: the loops INSIDE index_maps / split_blocks are the parallel ones (an if(false) region is inactive)
+#pragma omp parallel for schedule(dynamic, 1) if (nparts >= omp_get_max_threads())
     for (int32_t p = 0; p < nparts; ++p)
       og.run([&] {
-        index_maps(g[l].A, g[l].owner, g[l].oi, p, lev.parts[p]);
+        index_maps(g[l].A(), g[l].owner, g[l].oi, p, lev.parts[p]);
         gl[l][p].build(lev.parts[p].ghost_to_global);
       });
     og.rethrow();
@@ -1073,10 +1233,10 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
   for (int32_t l = 0; l < L; ++l) {
     Level& lev = h.levels[l];
     OmpGuard og;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) if (nparts >= omp_get_max_threads())
     for (int32_t p = 0; p < nparts; ++p) og.run([&] {
       PartLevel& pl = lev.parts[p];
-      split_blocks(g[l].A, pl.own_to_global, g[l].owner, g[l].oi.lid, p, pl.n_own, pl.n_ghost, gl[l][p],
+      split_blocks(g[l].A(), pl.own_to_global, g[l].owner, g[l].oi.lid, p, pl.n_own, pl.n_ghost, gl[l][p],
                    pl.blk[PAMG_A_OO], pl.blk[PAMG_A_OG]);
       fill_diag(pl);
       if (l + 1 < L) {
@@ -1095,8 +1255,8 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     build_halo_plans(lev, nparts);
   }
   tm.lap("localisation", L - 1);
-  h.n_coarse = g[L - 1].A.nrows;
-  dense_inverse(g[L - 1].A, h.coarse_inv);
+  h.n_coarse = g[L - 1].A().nrows;
+  dense_inverse(g[L - 1].A(), h.coarse_inv);
   tm.lap("dense inverse", L - 1);
   h.coarse_part_offset.assign(nparts + 1, 0);
   for (int32_t p = 0; p < nparts; ++p)

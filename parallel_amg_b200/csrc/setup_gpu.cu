@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -134,62 +135,101 @@ bool gpu_setup_available() {
   return true;
 }
 
-void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
-  if (A.ncols != B.nrows) throw std::runtime_error("gpu_spgemm: shape mismatch");
-  if (B.ncols >= (int64_t)1 << 31 || A.ncols >= (int64_t)1 << 31) throw std::runtime_error("gpu_spgemm: more than 2^31 columns");
-  const int64_t n = A.nrows;
-  C.nrows = n;
-  C.ncols = B.ncols;
-  C.ptr.assign(n + 1, 0);
-  C.col.clear();
-  C.val.clear();
-  // device copies (column ids as int32)
-  std::vector<int32_t> a_col32(A.col.begin(), A.col.end()), b_col32(B.col.begin(), B.col.end());
-  Buf<int64_t> dA_ptr, dB_ptr;
-  Buf<int32_t> dA_col, dB_col;
-  Buf<double> dA_val, dB_val;
-  dA_ptr.upload(A.ptr.data(), A.ptr.size());
-  dA_col.upload(a_col32.data(), a_col32.size());
-  dA_val.upload(A.val.data(), A.val.size());
-  dB_ptr.upload(B.ptr.data(), B.ptr.size());
-  dB_col.upload(b_col32.data(), b_col32.size());
-  dB_val.upload(B.val.data(), B.val.size());
-  std::vector<int32_t>().swap(a_col32);
-  std::vector<int32_t>().swap(b_col32);
+// device-resident CSR of the setup chain: int64 row pointers, int32 columns, fp64 values
+struct GpuMat {
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  Buf<int64_t> ptr;
+  Buf<int32_t> col;
+  Buf<double> val;
+};
 
-  // products per row on the host (cheap, also drives the chunking)
-  std::vector<int64_t> row_prod(n + 1, 0);
+GpuMat* gpu_upload(const Csr& A) {
+  if (A.ncols >= (int64_t)1 << 31) throw std::runtime_error("gpu setup: more than 2^31 columns");
+  std::unique_ptr<GpuMat> m(new GpuMat);
+  m->nrows = A.nrows;
+  m->ncols = A.ncols;
+  m->nnz = A.nnz();
+  std::vector<int32_t> col32(A.col.size());
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < n; ++i) {
-    int64_t s = 0;
-    for (int64_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) s += B.ptr[A.col[k] + 1] - B.ptr[A.col[k]];
-    row_prod[i + 1] = s;
+  for (int64_t k = 0; k < (int64_t)A.col.size(); ++k) col32[k] = (int32_t)A.col[k];
+  m->ptr.upload(A.ptr.data(), A.ptr.size());
+  m->col.upload(col32.data(), col32.size());
+  m->val.upload(A.val.data(), A.val.size());
+  return m.release();
+}
+
+void gpu_download(const GpuMat* m, Csr& C) {
+  C.nrows = m->nrows;
+  C.ncols = m->ncols;
+  C.ptr.resize(m->nrows + 1);
+  C.col.resize(m->nnz);
+  C.val.resize(m->nnz);
+  std::vector<int32_t> col32(m->nnz);
+  GK(cudaMemcpy(C.ptr.data(), m->ptr.p, (m->nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (m->nnz) {
+    GK(cudaMemcpy(col32.data(), m->col.p, m->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    GK(cudaMemcpy(C.val.data(), m->val.p, m->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < m->nnz; ++k) C.col[k] = col32[k];
+}
+
+void gpu_free(GpuMat* m) { delete m; }
+
+__global__ void k_row_products(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_col, const int64_t* __restrict__ b_ptr,
+                               int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  int64_t s = 0;
+  for (int64_t k = a_ptr[i]; k < a_ptr[i + 1]; ++k) s += b_ptr[a_col[k] + 1] - b_ptr[a_col[k]];
+  out[i] = s;
+}
+__global__ void k_set_u64_to_i64(const unsigned long long* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i < n) out[i] = (int64_t)in[i];
+}
+
+// C = A * B, everything on the device
+GpuMat* gpu_product(const GpuMat* A, const GpuMat* B) {
+  if (A->ncols != B->nrows) throw std::runtime_error("gpu_product: shape mismatch");
+  const int64_t n = A->nrows;
+  std::unique_ptr<GpuMat> C(new GpuMat);
+  C->nrows = n;
+  C->ncols = B->ncols;
+  // products per row -> chunking (host copy of the per-row counts: 8 bytes per row)
+  Buf<int64_t> d_rp;
+  d_rp.alloc(n + 1);
+  std::vector<int64_t> row_prod(n + 1, 0);
+  if (n) {
+    k_row_products<<<(int)((n + TB - 1) / TB), TB>>>(A->ptr.p, A->col.p, B->ptr.p, n, d_rp.p);
+    GK(cudaMemcpy(row_prod.data() + 1, d_rp.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
   }
   for (int64_t i = 0; i < n; ++i) row_prod[i + 1] += row_prod[i];
+  std::vector<int64_t> a_ptr(n + 1);
+  GK(cudaMemcpy(a_ptr.data(), A->ptr.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
   const char* be = getenv("PAMG_GPU_SETUP_BUDGET");
   const int64_t budget = be ? std::max<int64_t>(1 << 16, atoll(be)) : ((int64_t)384 << 20);  // products per chunk
 
   Buf<int64_t> d_cnt, d_off, d_head, d_pos;
   Buf<unsigned long long> d_keys, d_keys2, d_rowcnt;
-  Buf<double> d_vals, d_vals2, d_oval;
-  Buf<int32_t> d_ocol;
+  Buf<double> d_vals, d_vals2;
   Buf<char> d_tmp;
-  std::vector<unsigned long long> h_rowcnt;
-  std::vector<int32_t> h_col;
-  std::vector<double> h_val;
-  std::vector<std::vector<int32_t>> chunk_col;
-  std::vector<std::vector<double>> chunk_val;
-
-  int64_t r0 = 0;
+  d_rowcnt.alloc(std::max<int64_t>(n, 1));
+  GK(cudaMemset(d_rowcnt.p, 0, std::max<int64_t>(n, 1) * sizeof(unsigned long long)));
+  struct Chunk {
+    Buf<int32_t> col;
+    Buf<double> val;
+    int64_t n = 0;
+  };
+  std::vector<std::unique_ptr<Chunk>> chunks;
+  int64_t r0 = 0, total = 0;
   while (r0 < n) {
     int64_t r1 = r0 + 1;
     while (r1 < n && row_prod[r1 + 1] - row_prod[r0] <= budget) ++r1;
     const int64_t T = row_prod[r1] - row_prod[r0];
-    if (T >= (int64_t)1 << 40) throw std::runtime_error("gpu_spgemm: a single row produces too many products");
-    const int64_t e0 = A.ptr[r0], ne = A.ptr[r1] - e0, nr = r1 - r0;
-    std::vector<int32_t> ccol;
-    std::vector<double> cval;
-    h_rowcnt.assign(nr, 0);
+    if (T >= (int64_t)1 << 40) throw std::runtime_error("gpu_product: a single row produces too many products");
+    const int64_t e0 = a_ptr[r0], ne = a_ptr[r1] - e0, nr = r1 - r0;
+    std::unique_ptr<Chunk> ch(new Chunk);
     if (T > 0) {
       d_cnt.alloc(ne + 1);
       d_off.alloc(ne + 1);
@@ -199,10 +239,8 @@ void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
       d_vals2.alloc(T);
       d_head.alloc(T);
       d_pos.alloc(T);
-      d_rowcnt.alloc(nr);
-      GK(cudaMemset(d_rowcnt.p, 0, nr * sizeof(unsigned long long)));
       const int g_e = (int)((ne + TB - 1) / TB), g_t = (int)((T + TB - 1) / TB);
-      k_count<<<g_e, TB>>>(dA_ptr.p, dA_col.p, dB_ptr.p, e0, ne, d_cnt.p);
+      k_count<<<g_e, TB>>>(A->ptr.p, A->col.p, B->ptr.p, e0, ne, d_cnt.p);
       size_t tmp_bytes = 0, need = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, need, d_cnt.p, d_off.p, ne);
       tmp_bytes = need;
@@ -214,7 +252,7 @@ void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
       d_tmp.alloc(tmp_bytes);
       size_t tb = d_tmp.n;
       GK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_cnt.p, d_off.p, ne));
-      k_expand<<<g_e, TB>>>(dA_ptr.p, dA_col.p, dA_val.p, dB_ptr.p, dB_col.p, dB_val.p, r0, r1, e0, ne, d_off.p, d_keys.p, d_vals.p);
+      k_expand<<<g_e, TB>>>(A->ptr.p, A->col.p, A->val.p, B->ptr.p, B->col.p, B->val.p, r0, r1, e0, ne, d_off.p, d_keys.p, d_vals.p);
       tb = d_tmp.n;
       GK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_keys.p, d_keys2.p, d_vals.p, d_vals2.p, T, 0, end_bit));
       k_heads<<<g_t, TB>>>(d_keys2.p, T, d_head.p);
@@ -223,38 +261,48 @@ void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
       int64_t last_pos = 0, last_head = 0;
       GK(cudaMemcpy(&last_pos, d_pos.p + (T - 1), sizeof(int64_t), cudaMemcpyDeviceToHost));
       GK(cudaMemcpy(&last_head, d_head.p + (T - 1), sizeof(int64_t), cudaMemcpyDeviceToHost));
-      const int64_t nout = last_pos + last_head;
-      d_ocol.alloc(nout);
-      d_oval.alloc(nout);
-      k_compress<<<g_t, TB>>>(d_keys2.p, d_vals2.p, T, d_head.p, d_pos.p, d_ocol.p, d_oval.p, d_rowcnt.p);
+      ch->n = last_pos + last_head;
+      ch->col.alloc(ch->n);
+      ch->val.alloc(ch->n);
+      k_compress<<<g_t, TB>>>(d_keys2.p, d_vals2.p, T, d_head.p, d_pos.p, ch->col.p, ch->val.p, d_rowcnt.p + r0);
       GK(cudaGetLastError());
-      ccol.resize(nout);
-      cval.resize(nout);
-      GK(cudaMemcpy(ccol.data(), d_ocol.p, nout * sizeof(int32_t), cudaMemcpyDeviceToHost));
-      GK(cudaMemcpy(cval.data(), d_oval.p, nout * sizeof(double), cudaMemcpyDeviceToHost));
-      GK(cudaMemcpy(h_rowcnt.data(), d_rowcnt.p, nr * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
-    for (int64_t i = 0; i < nr; ++i) C.ptr[r0 + i + 1] = (int64_t)h_rowcnt[i];
-    chunk_col.push_back(std::move(ccol));
-    chunk_val.push_back(std::move(cval));
+    total += ch->n;
+    chunks.push_back(std::move(ch));
     r0 = r1;
   }
-  for (int64_t i = 0; i < n; ++i) C.ptr[i + 1] += C.ptr[i];
-  C.col.resize(C.ptr[n]);
-  C.val.resize(C.ptr[n]);
-  int64_t q = 0;
-  for (size_t k = 0; k < chunk_col.size(); ++k) {
-    const int64_t m = (int64_t)chunk_col[k].size();
-#pragma omp parallel for schedule(static)
-    for (int64_t j = 0; j < m; ++j) {
-      C.col[q + j] = chunk_col[k][j];
-      C.val[q + j] = chunk_val[k][j];
-    }
-    q += m;
-    std::vector<int32_t>().swap(chunk_col[k]);
-    std::vector<double>().swap(chunk_val[k]);
+  // row pointers from the per-row counts, then the chunks back to back
+  C->nnz = total;
+  C->ptr.alloc(n + 1);
+  C->col.alloc(total);
+  C->val.alloc(total);
+  {
+    Buf<int64_t> d_c64;
+    d_c64.alloc(n + 1);
+    GK(cudaMemset(d_c64.p, 0, (n + 1) * sizeof(int64_t)));
+    if (n) k_set_u64_to_i64<<<(int)((n + TB - 1) / TB), TB>>>(d_rowcnt.p, n, d_c64.p);
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, d_c64.p, C->ptr.p, n + 1);
+    d_tmp.alloc(need);
+    size_t tb = d_tmp.n;
+    GK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, d_c64.p, C->ptr.p, n + 1));
   }
-  if (q != C.ptr[n]) throw std::runtime_error("gpu_spgemm: internal count mismatch");
+  int64_t q = 0;
+  for (auto& ch : chunks) {
+    if (ch->n) {
+      GK(cudaMemcpy(C->col.p + q, ch->col.p, ch->n * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+      GK(cudaMemcpy(C->val.p + q, ch->val.p, ch->n * sizeof(double), cudaMemcpyDeviceToDevice));
+    }
+    q += ch->n;
+  }
+  GK(cudaDeviceSynchronize());
+  return C.release();
+}
+
+void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
+  std::unique_ptr<GpuMat> a(gpu_upload(A)), b(gpu_upload(B));
+  std::unique_ptr<GpuMat> c(gpu_product(a.get(), b.get()));
+  gpu_download(c.get(), C);
 }
 
 }  // namespace pamg
