@@ -229,10 +229,13 @@ int pamg_consistent(pamg_ctx* c, int32_t level, double* const* v);              
 int pamg_assemble(pamg_ctx* c, int32_t level, double* const* v);                    /* assemble!(v) |> wait */
 /* x <- nu sweeps of the configured smoother on A_level x = b (x is in/out) */
 int pamg_smooth(pamg_ctx* c, int32_t level, int32_t nu, const double* const* b, double* const* x);
-/* bc = R (b - A x)  (fused residual + restriction); r (may be NULL) receives b - A x */
+/* bc = R (b - A x); r (may be NULL) receives b - A x.  Two launches: the residual sweep (one pass over A, r written once)
+ * and the restriction (one pass over R; its epilogue also writes the coarse level's zero-guess first smoothing step).  A
+ * single-pass fusion would need every coarse row to recompute or stage the residuals of its R-support; DESIGN.md "a3" has
+ * the traffic count and the measurement behind keeping r in HBM. */
 int pamg_residual_restrict(pamg_ctx* c, int32_t level, const double* const* b,
                            const double* const* x, double* const* r, double* const* bc);
-/* x += P ec (fused prolongation + correction) */
+/* x += P ec (prolongation and correction in one pass over P: the row epilogue adds into x) */
 int pamg_prolong_correct(pamg_ctx* c, int32_t level, const double* const* ec, double* const* x);
 int pamg_dot(pamg_ctx* c, int32_t level, const double* const* u, const double* const* v, double* out);
 /* x = V-cycle(b) from x = 0 (the preconditioner apply, `ldiv!(x, P, b)` / `solve!(x,S,b)`) */

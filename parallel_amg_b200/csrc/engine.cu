@@ -232,11 +232,15 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     const int C = 32 * rpt;
     SellHost sh;
     int sigma = o.sell_sigma > 0 ? o.sell_sigma : 1;
+    int forced_sigma = 0;  // experiments: sorting window of one operator class (rows), overriding the automatic choice
+    if (which == PAMG_P_OO && getenv("PAMG_P_SIGMA")) forced_sigma = atoi(getenv("PAMG_P_SIGMA"));
+    if (which == PAMG_R_OO && getenv("PAMG_R_SIGMA")) forced_sigma = atoi(getenv("PAMG_R_SIGMA"));
+    if (forced_sigma > 0) sigma = forced_sigma;
     sell_layout(m, C, sigma, sh, false);
     // auto sigma: sort inside windows only when the unsorted padding is large (the permutation costs more than
     // ~20 % padding does: P at 256^3 runs 0.228 ms unsorted with 1.16x fill, 0.240 ms sorted with 1.01x)
     const double sort_fill = getenv("PAMG_SELL_SORT_FILL") ? atof(getenv("PAMG_SELL_SORT_FILL")) : 1.25;
-    if (o.sell_sigma <= 0 && sh.fill > sort_fill) {
+    if (o.sell_sigma <= 0 && forced_sigma <= 0 && sh.fill > sort_fill) {
       SellHost s2;
       sell_layout(m, C, 64 * C, s2, false);
       if (s2.fill < sh.fill - 0.02) sigma = 64 * C;
@@ -484,6 +488,8 @@ struct Engine::Impl {
   int unified = 0;          // fused persistent SELL launches without role CTAs: bit mask over operator classes (env PAMG_UNIFIED;
                             // 1 A short rows, 2 A long rows, 4 P, 8 R).  Off: measured +67 us per iteration on 8 GPUs (profiles/r02)
   bool fold_check = false;  // the convergence check runs inside k_update_xr / k_pcg_init (every local part alone on its GPU)
+  bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
+  int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
   bool counting = true;
@@ -634,9 +640,16 @@ void launch_csr(int mode, bool dot, int lanes, CsrView A, const LaunchArgs& L) {
   });
 }
 
-void launch_stream(int mode, bool dot, StreamView A, const LaunchArgs& L) {
+// long_rows: mean row length >= 48 -> the phase-B variant with 16 lanes per row (kernels.cuh k_spmv_stream LONG)
+void launch_stream(int mode, bool dot, bool long_rows, StreamView A, const LaunchArgs& L) {
   dispatch_mode(mode, dot, [&](auto md, auto dt) {
-    auto k = k_spmv_stream<decltype(md)::value, decltype(dt)::value>;
+    constexpr int MD = decltype(md)::value;
+    constexpr bool DT = decltype(dt)::value;
+    using Kern = void (*)(StreamView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
+    Kern k = k_spmv_stream<MD, DT, false>;
+    if constexpr (!DT) {
+      if (long_rows) k = k_spmv_stream<MD, false, true>;
+    }
     k<<<main_grid(L, (const void*)k), BLOCK, 0, L.s>>>(A, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
   });
 }
@@ -645,7 +658,8 @@ void launch_stream(int mode, bool dot, StreamView A, const LaunchArgs& L) {
 // 1 = <RPT 2, U 2, 5 CTAs/SM>, 2 = <RPT 1, U 4, 6 CTAs/SM> (needs the C = 32 layout).
 // try_unified: fused launch of one part per GPU -- run without role CTAs when every CTA's share of the boundary rows fits
 // (kernels.cuh "Unified CTA roles"); *was_unified reports the decision.
-void launch_sell(int mode, bool dot, int rpt, int short_variant, SellView A, LaunchArgs L, bool try_unified, bool* was_unified) {
+void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, SellView A, LaunchArgs L, bool try_unified,
+                 bool* was_unified) {
   dispatch_mode(mode, dot, [&](auto md, auto dt) {
     constexpr int MD = decltype(md)::value;
     constexpr bool DT = decltype(dt)::value;
@@ -654,6 +668,9 @@ void launch_sell(int mode, bool dot, int rpt, int short_variant, SellView A, Lau
     if constexpr (MD == M_ADD && !DT) {
       if (short_variant == 1 && rpt == 2) k = (Kern)k_spmv_sell<2, M_ADD, false, 2, 5>;
       if (short_variant == 2 && rpt == 1) k = (Kern)k_spmv_sell<1, M_ADD, false, 4, 6>;
+    }
+    if constexpr (!DT) {  // L2 prefetch of the slice two iterations ahead (persistent launches of the latency-bound operators)
+      if (prefetch && rpt == 2 && short_variant == 0) k = (Kern)k_spmv_sell<2, MD, false, 4, 3, 2>;
     }
     int grid = 0;
     *was_unified = false;
@@ -764,7 +781,10 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     // PAMG_UNIFIED bit mask: 1 = A with short rows, 2 = A with long rows, 4 = P, 8 = R
     const int uni_bit = op.which == PAMG_P_OO ? 4 : op.which == PAMG_R_OO ? 8 : (mean_nnz <= 12.0 ? 1 : 2);
     const bool try_unified = fused && (I.unified & uni_bit) && m.sell_rpt && (fh.n_pack > 0 || fh.n_bnd > 0);
-    const bool bounded = I.persistent && m.sell_rpt && (mean_nnz <= 12.0 || try_unified);
+    // PAMG_SELL_PF bit mask: 1 = P, 2 = A with long rows, 4 = R (these then run persistent, which the prefetch needs)
+    const int pf_bit = op.which == PAMG_P_OO ? 1 : op.which == PAMG_R_OO ? 4 : (mean_nnz > 12.0 ? 2 : 0);
+    const bool prefetch = I.persistent && m.sell_rpt == 2 && (I.sell_pf & pf_bit) && !op.dot && !try_unified;
+    const bool bounded = I.persistent && m.sell_rpt && (mean_nnz <= 12.0 || try_unified || prefetch);
     LaunchArgs L{0, bounded || op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
     L.fh.v = xin[i];
     int n_main;
@@ -778,10 +798,10 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     L.grid = std::max(n_main, 1);
     bool was_unified = false;
     if (m.sell_rpt)
-      launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, m.slview(), L, try_unified,
-                  &was_unified);
+      launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
+                  try_unified, &was_unified);
     else if (m.stream)
-      launch_stream(op.mode, op.dot, m.sview(), L);
+      launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
       launch_csr(op.mode, op.dot, m.lanes, m.view(), L);
     if (I.naming) {
@@ -1121,6 +1141,8 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
     if (const char* pe = getenv("PAMG_PERSISTENT")) I.persistent = atoi(pe) != 0;
     if (const char* ue = getenv("PAMG_UNIFIED")) I.unified = atoi(ue);
     if (const char* te = getenv("PAMG_FUSED_TAIL")) I.fused_tail = atoi(te) != 0;
+    if (const char* le = getenv("PAMG_STREAM_LONG")) I.stream_long = atoi(le) != 0;
+    if (const char* pe2 = getenv("PAMG_SELL_PF")) I.sell_pf = atoi(pe2);
     if (const char* te = getenv("PAMG_TAIL_CTAS")) I.tail_ctas = std::max(1, atoi(te));
     I.alone = alone;
     {

@@ -661,7 +661,12 @@ __device__ __forceinline__ void stream_row_block(const StreamView& A, const doub
   if (more) __syncthreads();  // prod is reused by the next row block
 }
 
-template <int MODE, bool DOT>
+// LONG (rows of >= 48 entries on average: the restriction operators of the coarse levels, 240 entries per row at 256^3, and
+// the Galerkin matrices of the tail): a row block then holds a dozen rows, and one thread per row leaves 244 of 256 threads
+// idle through a 240-step dependent add chain (restrict R1: 68 us for 146 MB).  Phase B there gives every row S_LB lanes:
+// lane j adds the products k = j, j + S_LB, ... in ascending order, then a fixed xor tree over the lanes: deterministic,
+// but not the oracle's left-to-right order (1e-16 relative, like the sub-warp CSR family).
+template <int MODE, bool DOT, bool LONG = false>
 __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const double* __restrict__ x, EpiArgs a, DevState* st,
                                                         FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
@@ -729,6 +734,38 @@ __global__ void __launch_bounds__(BLOCK, 4) k_spmv_stream(StreamView A, const do
       }
     }
     __syncthreads();
+    if (LONG) {  // S_LB lanes per row, BLOCK / S_LB rows per pass (block-uniform trip count: full-mask shuffles)
+      constexpr int S_LB = 16;
+      const int lane = t & (S_LB - 1);
+      for (int rr0 = 0; rr0 < nr; rr0 += BLOCK / S_LB) {
+        const int rr = rr0 + t / S_LB;
+        const bool valid = rr < nr;
+        const int row = r0 + rr;
+        int qb = 0, qe = 0;
+        unsigned char sk2 = 0;
+        double f_in0 = 0.0, f_in1 = 0.0, f_w = 0.0, f_aux = 0.0, f_dot = 0.0;
+        if (valid) {
+          qb = A.ptr[row] - ea;
+          qe = A.ptr[row + 1] - ea;
+          if (lane == 0) {  // the epilogue operands travel while the lanes add
+            if (fh.skip) sk2 = fh.skip[row];
+            if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) f_in0 = a.in0[row];
+            if (MODE == M_JACOBI || MODE == M_CHEB) f_in1 = a.in1[row];
+            if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) f_w = a.w[row];
+            if (MODE == M_CHEB && a.aux) f_aux = a.aux[row];
+            if (DOT) f_dot = a.dotv[row];
+          }
+        }
+        double s = 0.0;
+        for (int k = qb + lane; k < qe; k += S_LB) s += prod[k];
+#pragma unroll
+        for (int o = S_LB / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (valid && lane == 0 && !sk2) {
+          const double res = stream_epilogue<MODE>(a, row, s, f_in0, f_in1, f_w, f_aux);
+          if (DOT) acc += f_dot * res;
+        }
+      }
+    } else
     // phase B: thread t owns rows t, t + BLOCK, ...; products summed in column order
 #pragma unroll
     for (int q = 0; q < S_CHUNKS; ++q) {
@@ -873,7 +910,11 @@ __device__ __forceinline__ double unified_bnd_ghost(const FusedHalo& fh, const E
 // production kernels (RPT = 2: 4 x 128-bit value loads + 4 x 64-bit column loads per thread and step, 3 CTAs/SM).  The
 // short-row instantiations <2, M_ADD, false, 2, 5> and <1, M_ADD, false, 4, 6> (48 / 40 registers) were built for the
 // prolongators (rows of 1-8 entries) and measured in round 2: no gain (profiles/r02_kernel_sweep.md), kept for the record.
-template <int RPT, int MODE, bool DOT, int U = (RPT == 1 ? 8 : 4), int MINB = (RPT == 1 ? 4 : 3)>
+// PF > 0 (persistent launches only): while a warp works on slice i it requests the entries of the slice it will reach PF
+// iterations later into L2 (prefetch.global.L2, no register, no scoreboard), so that the dependent chain of a slice
+// -- extents -> columns/values -> gathers -> epilogue -- starts from L2 instead of HBM latency.  For the latency-bound
+// operators (prolongators: 1-8 entries per row, 37 % warps active, 56 % DRAM throughput in ncu).
+template <int RPT, int MODE, bool DOT, int U = (RPT == 1 ? 8 : 4), int MINB = (RPT == 1 ? 4 : 3), int PF = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell(SellView A, const double* __restrict__ x, EpiArgs a, DevState* st,
                                                       FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
@@ -899,6 +940,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell(SellView A, const dou
   for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
     const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
     const int slot0 = sl * (32 * RPT) + lane * RPT;
+    int pf0 = 0, pfw = 0;  // extents of the slice to prefetch (requested here, used behind the entry loop)
+    if (PF > 0) {
+      const int sp = sl + PF * n_main * wpb;
+      if (sp < A.nslices) {
+        pf0 = A.slice_off[sp];
+        pfw = A.slice_off[sp + 1] - pf0;
+      }
+    }
     // Nothing but the row sums stays in registers across the entry loop: the epilogue operands, the skip
     // flags and (with a permutation) the row ids are prefetched into L1 here and loaded after the loop.
 #pragma unroll
@@ -941,6 +990,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell(SellView A, const dou
 #pragma unroll
           for (int k = 0; k < RPT; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(sv_get(v[u], k), xv[u][k]));
         }
+    }
+    if (PF > 0) {
+      const char* pv = reinterpret_cast<const char*>(reinterpret_cast<const V*>(A.val) + (size_t)pf0 * 32 + lane);
+      const char* pc = reinterpret_cast<const char*>(reinterpret_cast<const I*>(A.col) + (size_t)pf0 * 32 + lane);
+      for (int j = 0; j < pfw; ++j) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + (size_t)j * 32 * sizeof(V)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + (size_t)j * 32 * sizeof(I)));
+      }
     }
     double contrib = 0.0;
 #pragma unroll

@@ -125,8 +125,10 @@ int bits_for(uint64_t v) {
 }  // namespace
 
 bool gpu_setup_available() {
+  // opt-in: with the host CSR in int64 / pageable memory the PCIe marshalling eats what the device products save
+  // (256^3: 10.4 s with the GPU chain vs 9.5 s on 16 host cores, profiles/r02_setup_timing.txt)
   const char* e = getenv("PAMG_GPU_SETUP");
-  if (e && atoi(e) == 0) return false;
+  if (!e || atoi(e) == 0) return false;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();

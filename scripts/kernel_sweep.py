@@ -41,13 +41,29 @@ CONFIGS = {
 }
 # A/B switches of the engine (read at device_init): name -> environment
 ENVS = {
-    "auto-r1": dict(PAMG_P_KERNEL="0", PAMG_RENUMBER="0"),       # round-1 behaviour
+    "auto-r1": dict(PAMG_P_KERNEL="0", PAMG_RENUMBER="0", PAMG_STREAM_LONG="0"),       # round-1 behaviour
     "auto-p0": dict(PAMG_P_KERNEL="0"),
     "auto-p2": dict(PAMG_P_KERNEL="2"),
     "auto-nore": dict(PAMG_RENUMBER="0"),
     "auto-nosort": dict(PAMG_SELL_SORT_FILL="9"),
     "auto-p2-nosort": dict(PAMG_P_KERNEL="2", PAMG_SELL_SORT_FILL="9"),
-    "auto-w16k": dict(PAMG_RENUMBER_WINDOW="16384"),
+    "auto-w16k": dict(PAMG_RENUMBER="1", PAMG_RENUMBER_WINDOW="16384"),
+    "auto-renum": dict(PAMG_RENUMBER="1"),
+    "auto-w512": dict(PAMG_RENUMBER="1", PAMG_RENUMBER_WINDOW="512"),
+    "auto-w1024": dict(PAMG_RENUMBER="1", PAMG_RENUMBER_WINDOW="1024"),
+    "auto-p1": dict(PAMG_P_KERNEL="1"),
+    "auto-nolong": dict(PAMG_STREAM_LONG="0"),
+    "auto-psig256": dict(PAMG_P_SIGMA="256"),
+    "auto-psig512": dict(PAMG_P_SIGMA="512"),
+    "auto-psig1024": dict(PAMG_P_SIGMA="1024"),
+    "auto-rsig4096": dict(PAMG_R_SIGMA="4096"),
+    "auto-sort1.1": dict(PAMG_SELL_SORT_FILL="1.1"),
+    "auto-pf1": dict(PAMG_SELL_PF="1"),
+    "auto-pf3": dict(PAMG_SELL_PF="3"),
+    "auto-pf5": dict(PAMG_SELL_PF="5"),
+    "auto-pf7": dict(PAMG_SELL_PF="7"),
+    "auto-pf7-w512": dict(PAMG_SELL_PF="7", PAMG_RENUMBER="1", PAMG_RENUMBER_WINDOW="512"),
+    "auto-pf1-w512": dict(PAMG_SELL_PF="1", PAMG_RENUMBER="1", PAMG_RENUMBER_WINDOW="512"),
 }
 for k in ENVS:
     CONFIGS[k] = dict(spmv_format=L.FORMAT_AUTO)
@@ -57,7 +73,7 @@ else:
     CONFIGS = {k: v for k, v in CONFIGS.items() if k not in ENVS}
 res = {}
 for name, kw in CONFIGS.items():
-    for k in ("PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW"):
+    for k in ("PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW", "PAMG_STREAM_LONG", "PAMG_P_SIGMA", "PAMG_R_SIGMA", "PAMG_SELL_PF"):
         os.environ.pop(k, None)
     os.environ.update(ENVS.get(name, {}))
     c.set_kernel_options(**kw)
