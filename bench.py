@@ -147,12 +147,12 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
 
 
-def cpu_solve_timed(c, nparts, b_parts, reps):
+def cpu_solve_timed(c, nparts, b_parts, reps, threads=None):
     """The oracle's C/OpenMP solve phase on the host cores, same hierarchy (copied out through the C ABI), same rhs."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     from parallel_amg_b200 import _lib as L
-    L.set_num_threads(os.cpu_count() or 1)   # launchers export OMP_NUM_THREADS=1; the oracle shares the process's OpenMP runtime
+    L.set_num_threads(threads or os.cpu_count() or 1)   # launchers export OMP_NUM_THREADS=1; the oracle shares the process's OpenMP runtime
     co = c_oracle.COracle.from_product_context(c, nparts)
     times, it, hist = [], 0, None
     for _ in range(reps):
@@ -381,39 +381,56 @@ def measure(workload, args, rank, world, local_rank, steps, warmup, headline):
         dist.all_reduce(tl)
         launches = int(tl.item())
 
+    # While rank 0 runs the CPU oracle the other ranks must SLEEP: ranks spinning in an NCCL barrier take a core each and
+    # an oversubscribed OpenMP team is an order of magnitude slower (measured: 40 s instead of 3 s per solve on 8 ranks).
+    flag = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp",
+                        f"pamg_bench_{os.environ.get('MASTER_PORT', '0')}_{workload}_{args.gpus}.cpu_done")
+    if world > 1:
+        if rank == 0 and os.path.exists(flag):
+            os.remove(flag)
+        barrier()
     rec = None
     if rank == 0:
-        # ---- the same solve on the host cores by the C oracle: CPU baseline AND parity of the timed solve ---------
-        cpu = None
-        parity = dict(iters=int(it), oracle_iters=None, iters_match=None, history_match=None)
-        if not args.no_cpu_baseline and n <= 40_000_000:   # the 512^3 secondary would copy 37 GB of hierarchy for the oracle
-            own_all = [c.index_maps(0, p)[0] for p in range(nparts)]
-            reps = args.cpu_reps if headline else 1
-            times, it_cpu, hist_cpu = cpu_solve_timed(c, nparts, [b[o] for o in own_all], reps)
-            cores = os.cpu_count()
-            cpu = dict(value=n / min(times), unit="DOF/s", cores=cores, kind="port",
-                       sample=f"{reps} whole solve(s) ({it_cpu} iterations each) of the same workload on the same {nparts}-part hierarchy, best one; "
-                              "C/OpenMP oracle port on all host cores (no reference code exists)",
-                       seconds=[round(t, 3) for t in times], iters=int(it_cpu))
-            hmatch = bool(len(hist) == len(hist_cpu) and np.allclose(hist, hist_cpu, rtol=1e-7))
-            parity = dict(iters=int(it), oracle_iters=int(it_cpu), iters_match=bool(it == it_cpu), history_match=hmatch)
-            assert it == it_cpu, f"PCG iterations differ from the C oracle: device {it}, oracle {it_cpu}"
-            assert hmatch, "PCG residual history differs from the C oracle's beyond 1e-7 relative"
-        peak, peak_src = peaks()
-        dom = kern["spmv A0"]
-        rec = dict(
-            value=n * steps / (dev_ms * 1e-3), ms_per_step=dev_ms / steps, n=int(n), iters=int(it), levels=c.num_levels(),
-            vcycle_ms=float(np.mean(vc)), wall_ms_per_step=wall_ms / steps, true_residual_rel=true_rel, solution_max_err=sol_err,
-            roofline=dict(bound="hbm", kernel=kname + " level 0: y = A x, fp64 values / int32 columns", achieved=dom["gbs"],
-                          peak=peak, unit="GB/s", frac=dom["gbs"] / peak, peak_source=peak_src, traffic=ncu_traffic(workload, args.gpus),
-                          algorithmic_bytes_per_launch=dom["bytes"], ms_per_launch=dom["ms"],
-                          frac_of_nominal_8TBs=dom["gbs"] / 8000.0),
-            kernels=kern,
-            e2e=dict(value=n * steps / (e2e_ms * 1e-3), unit="DOF/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
-                     ms_per_step=e2e_ms / steps),
-            gpu_launches=int(launches), clocks=clocks, cpu_baseline=cpu, parity=parity,
-            host_setup_s=round(setup_s, 1), host_setup="rank 0 + shared-memory hand-off" if share else "every rank")
+        try:
+            # ---- the same solve on the host cores by the C oracle: CPU baseline AND parity of the timed solve ---------
+            cpu = None
+            parity = dict(iters=int(it), oracle_iters=None, iters_match=None, history_match=None)
+            if not args.no_cpu_baseline and n <= 40_000_000:   # the 512^3 secondary would copy 37 GB of hierarchy for the oracle
+                own_all = [c.index_maps(0, p)[0] for p in range(nparts)]
+                reps = args.cpu_reps if headline else 1
+                cores = max(1, (os.cpu_count() or 1) - (world - 1))   # the sleeping ranks still own a helper thread each
+                times, it_cpu, hist_cpu = cpu_solve_timed(c, nparts, [b[o] for o in own_all], reps, threads=cores)
+                cpu = dict(value=n / min(times), unit="DOF/s", cores=cores, kind="port",
+                           sample=f"{reps} whole solve(s) ({it_cpu} iterations each) of the same workload on the same {nparts}-part hierarchy, best one; "
+                                  f"C/OpenMP oracle port on {cores} host threads (no reference code exists)",
+                           seconds=[round(t, 3) for t in times], iters=int(it_cpu))
+                hmatch = bool(len(hist) == len(hist_cpu) and np.allclose(hist, hist_cpu, rtol=1e-7))
+                parity = dict(iters=int(it), oracle_iters=int(it_cpu), iters_match=bool(it == it_cpu), history_match=hmatch)
+                assert it == it_cpu, f"PCG iterations differ from the C oracle: device {it}, oracle {it_cpu}"
+                assert hmatch, "PCG residual history differs from the C oracle's beyond 1e-7 relative"
+            peak, peak_src = peaks()
+            dom = kern["spmv A0"]
+            rec = dict(
+                value=n * steps / (dev_ms * 1e-3), ms_per_step=dev_ms / steps, n=int(n), iters=int(it), levels=c.num_levels(),
+                vcycle_ms=float(np.mean(vc)), wall_ms_per_step=wall_ms / steps, true_residual_rel=true_rel, solution_max_err=sol_err,
+                roofline=dict(bound="hbm", kernel=kname + " level 0: y = A x, fp64 values / int32 columns", achieved=dom["gbs"],
+                              peak=peak, unit="GB/s", frac=dom["gbs"] / peak, peak_source=peak_src, traffic=ncu_traffic(workload, args.gpus),
+                              algorithmic_bytes_per_launch=dom["bytes"], ms_per_launch=dom["ms"],
+                              frac_of_nominal_8TBs=dom["gbs"] / 8000.0),
+                kernels=kern,
+                e2e=dict(value=n * steps / (e2e_ms * 1e-3), unit="DOF/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
+                         ms_per_step=e2e_ms / steps),
+                gpu_launches=int(launches), clocks=clocks, cpu_baseline=cpu, parity=parity,
+                host_setup_s=round(setup_s, 1), host_setup="rank 0 + shared-memory hand-off" if share else "every rank")
+        finally:   # whatever happens here, the sleeping ranks must be released
+            if world > 1:
+                open(flag, "w").close()
+    elif world > 1:
+        while not os.path.exists(flag):
+            time.sleep(0.05)
     barrier()
+    if world > 1 and rank == 0:
+        os.remove(flag)
     c.close()
     return rec
 
