@@ -489,6 +489,7 @@ struct Engine::Impl {
                             // 1 A short rows, 2 A long rows, 4 P, 8 R).  Off: measured +67 us per iteration on 8 GPUs (profiles/r02)
   bool fold_check = false;  // the convergence check runs inside k_update_xr / k_pcg_init (every local part alone on its GPU)
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
+  int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
@@ -659,7 +660,7 @@ void launch_stream(int mode, bool dot, bool long_rows, StreamView A, const Launc
 // try_unified: fused launch of one part per GPU -- run without role CTAs when every CTA's share of the boundary rows fits
 // (kernels.cuh "Unified CTA roles"); *was_unified reports the decision.
 void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, SellView A, LaunchArgs L, bool try_unified,
-                 bool* was_unified) {
+                 int unified_mode, bool* was_unified) {
   dispatch_mode(mode, dot, [&](auto md, auto dt) {
     constexpr int MD = decltype(md)::value;
     constexpr bool DT = decltype(dt)::value;
@@ -674,7 +675,14 @@ void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, 
     }
     int grid = 0;
     *was_unified = false;
-    if (try_unified && rpt == 2) {
+    if (try_unified && rpt == 2 && unified_mode == 2) {  // "lite": pack CTAs + work CTAs that finish with the boundary role
+      k = (Kern)k_spmv_sell_uni<MD, DT>;
+      const int n_work = std::max(1, std::min(L.grid, std::min(resident_ctas((const void*)k), RED_GRID)));
+      L.fh.unified = 2;
+      if (L.fh.n_bnd > 0) L.fh.n_bnd = n_work;
+      grid = L.fh.n_pack + n_work;
+      *was_unified = true;
+    } else if (try_unified && rpt == 2) {
       k = (Kern)k_spmv_sell_uni<MD, DT>;
       const int n_work = std::max(1, std::min(L.grid, std::min(resident_ctas((const void*)k), RED_GRID)));
       const int share = (L.fh.B.n + n_work - 1) / n_work;
@@ -799,7 +807,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     bool was_unified = false;
     if (m.sell_rpt)
       launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
-                  try_unified, &was_unified);
+                  try_unified, I.unified_mode, &was_unified);
     else if (m.stream)
       launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
@@ -1140,6 +1148,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
                       "operator); the peer-memory exchange protocol needs symmetric neighbour sets on multi-GPU layouts");
     if (const char* pe = getenv("PAMG_PERSISTENT")) I.persistent = atoi(pe) != 0;
     if (const char* ue = getenv("PAMG_UNIFIED")) I.unified = atoi(ue);
+    if (const char* ue = getenv("PAMG_UNIFIED_MODE")) I.unified_mode = atoi(ue) == 2 ? 2 : 1;
     if (const char* te = getenv("PAMG_FUSED_TAIL")) I.fused_tail = atoi(te) != 0;
     if (const char* le = getenv("PAMG_STREAM_LONG")) I.stream_long = atoi(le) != 0;
     if (const char* pe2 = getenv("PAMG_SELL_PF")) I.sell_pf = atoi(pe2);

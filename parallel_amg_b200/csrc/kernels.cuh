@@ -1022,7 +1022,16 @@ __global__ void __launch_bounds__(BLOCK, 3) k_spmv_sell_uni(SellView A, const do
                                                           FusedHalo fh, double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
   trace_mark(st);
-  const int n_main = (int)gridDim.x, bid = (int)blockIdx.x;
+  // fh.unified == 1: every CTA packs, does boundary rows (own part before, ghost part behind the slices) and slices.
+  // fh.unified == 2 ("lite"): the first fh.n_pack CTAs are pack CTAs as in k_spmv_sell; the others stream their static
+  // share of the slices and THEN run the whole boundary role over fh.n_bnd = all work CTAs (the flags are there by then).
+  const bool lite = fh.unified == 2;
+  if (lite && (int)blockIdx.x < fh.n_pack) {
+    pack_role(fh, st, blockIdx.x);
+    if (DOT) dot_finish(0.0, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+    return;
+  }
+  const int n_main = lite ? (int)gridDim.x - fh.n_pack : (int)gridDim.x, bid = lite ? (int)blockIdx.x - fh.n_pack : (int)blockIdx.x;
   constexpr int RPT = 2, U = 4;
   using V = typename SellVec<RPT>::V;
   using I = typename SellVec<RPT>::I;
@@ -1031,8 +1040,10 @@ __global__ void __launch_bounds__(BLOCK, 3) k_spmv_sell_uni(SellView A, const do
   __shared__ double s_acc[DOT ? BLOCK : 1];  // per-thread running dot (each thread touches only its own slot)
   __shared__ double s_bnd[BLOCK];            // unified roles: own-column sums of this CTA's boundary rows
   if (DOT) s_acc[threadIdx.x] = 0.0;
-  if (fh.n_pack > 0) pack_role(fh, st, bid);
-  if (fh.n_bnd > 0) unified_bnd_own<MODE, DOT>(fh, x, s_bnd, bid);
+  if (!lite) {
+    if (fh.n_pack > 0) pack_role(fh, st, bid);
+    if (fh.n_bnd > 0) unified_bnd_own<MODE, DOT>(fh, x, s_bnd, bid);
+  }
   for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
     const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
     const int slot0 = sl * (32 * RPT) + lane * RPT;
@@ -1093,7 +1104,7 @@ __global__ void __launch_bounds__(BLOCK, 3) k_spmv_sell_uni(SellView A, const do
     if (DOT) s_acc[threadIdx.x] += contrib;  // in shared memory: a register live across the entry loop costs its load batching
   }
   double bacc = 0.0;
-  if (fh.n_bnd > 0) bacc = unified_bnd_ghost<MODE, DOT>(fh, a, st, s_bnd, bid, n_main);
+  if (fh.n_bnd > 0) bacc = lite ? boundary_role<MODE, DOT>(fh, x, a, st, bid) : unified_bnd_ghost<MODE, DOT>(fh, a, st, s_bnd, bid, n_main);
   if (DOT) dot_finish(s_acc[threadIdx.x] + bacc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }
 

@@ -29,13 +29,15 @@ def main():
              ((40, 40, 40), {"nu_pre": 2, "nu_post": 2}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {"PAMG_UNIFIED": "15"}),
              ((40, 40, 40), {"smoother": "chebyshev", "cheb_degree": 3}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {"PAMG_UNIFIED": "15"}),
              ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {}),
+             ((40, 40, 40), {"nu_pre": 2, "nu_post": 2}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {"PAMG_UNIFIED": "15", "PAMG_UNIFIED_MODE": "2"}),
+             ((48, 40, 36), {"smoother": "l1jacobi"}, dict(spmv_format=L.FORMAT_SELL, tail_rows=0), {"PAMG_UNIFIED": "15", "PAMG_UNIFIED_MODE": "2"}),
              ((48, 40, 36), {}, dict(spmv_format=L.FORMAT_SELL, sell_sigma=256, tail_rows=0), {"PAMG_UNIFIED": "15"}),
              # replicated tail: one launch per operation / separate convergence check / renumbered coarse levels
              ((40, 40, 40), {}, {}, {"PAMG_FUSED_TAIL": "1"}), ((40, 40, 40), {}, {}, {"PAMG_FOLD_CHECK": "0"}),
              ((40, 40, 40), {"cycle": "w", "coarse_size": 40}, dict(tail_rows=600), {}),
              ((40, 40, 40), {"nu_pre": 0, "nu_post": 2}, {}, {}),
              ((40, 40, 40), {}, dict(spmv_format=L.FORMAT_SELL, tail_rows=600), {"PAMG_RENUMBER": "1", "PAMG_RENUMBER_WINDOW": "256"}))
-    switches = ("PAMG_UNIFIED", "PAMG_FUSED_TAIL", "PAMG_FOLD_CHECK", "PAMG_RENUMBER", "PAMG_RENUMBER_WINDOW")
+    switches = ("PAMG_UNIFIED", "PAMG_UNIFIED_MODE", "PAMG_FUSED_TAIL", "PAMG_FOLD_CHECK", "PAMG_RENUMBER", "PAMG_RENUMBER_WINDOW")
     for dims, oopts, kopts, env in cases:
         for k in switches:
             os.environ.pop(k, None)
