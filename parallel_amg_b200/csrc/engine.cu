@@ -383,9 +383,11 @@ struct ArenaLayout {
 int tail_level_of(const Hierarchy& h) {
   const int L = (int)h.levels.size();
   if (L <= 1) return 0;
-  if (h.nparts == 1 || h.opts.tail_rows <= 0) return L - 1;
+  int64_t tail_rows = h.opts.tail_rows;
+  if (const char* e = getenv("PAMG_TAIL_ROWS")) tail_rows = std::min<int64_t>(tail_rows, atoll(e));  // experiments: only lowering is safe
+  if (h.nparts == 1 || tail_rows <= 0) return L - 1;
   for (int l = 1; l < L; ++l)
-    if (h.levels[l].n_global <= h.opts.tail_rows) return l;
+    if (h.levels[l].n_global <= tail_rows) return l;
   return L - 1;
 }
 
