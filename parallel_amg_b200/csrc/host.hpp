@@ -88,6 +88,10 @@ GpuMat* gpu_upload(const Csr& A);
 GpuMat* gpu_product(const GpuMat* A, const GpuMat* B);
 void gpu_download(const GpuMat* m, Csr& C);
 void gpu_free(GpuMat* m);
+GpuMat* gpu_smooth_prolongator(const GpuMat* F, const GpuMat* P0, const double* w_host);  // P0 + diag(w) (F P0), merged by column
+GpuMat* gpu_transpose(const GpuMat* A);                                                   // ascending columns in every row
+void gpu_setup_begin();  // pinned staging buffers for the transfers of one setup
+void gpu_setup_end();
 
 // ---- setup ------------------------------------------------------------------------------------
 // Builds every level (global matrices internally, then the per-part split format).

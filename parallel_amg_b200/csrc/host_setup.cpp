@@ -540,9 +540,11 @@ static int64_t aggregate_part(const Csr& A, const std::vector<int32_t>& owner, c
 // ------------------------------------------------------------------------------------------
 // P0: tentative prolongator (n x nc, sorted columns): one unit entry per row for scalar problems, the
 // per-aggregate Q factors of the near-nullspace for block problems.
-// dA: the device copy of A when the GPU chain is on (used for S = A P0 when no filtering makes A_F = A), else nullptr
+// dA: the device copy of A when the GPU chain is on, else nullptr.  With it the whole smoothing runs on the device
+// (S = A_F P0, merge) and *dP_out keeps the smoothed prolongator resident for the transpose and the Galerkin product.
 static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double eps,
-                              const std::vector<double>& absdiag, Csr& P, double* omega_out, bool gpu, const GpuMat* dA) {
+                              const std::vector<double>& absdiag, Csr& P, double* omega_out, bool gpu, const GpuMat* dA,
+                              GpuMat** dP_out) {
   const int64_t n = A.nrows;
   // filtered matrix A_F (weak off-diagonals lumped into the diagonal); eps == 0 => A_F = A
   Csr AF;
@@ -603,22 +605,32 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
   *omega_out = omega;
 
   // S = A_F P0 (structural product, encounter-order sums), then P = P0 - omega D_F^-1 S merged by column
-  Csr S;
-  bool done = false;
-  if (gpu && dA && F == &A) {  // A is already resident: upload only P0, download only S
-    GpuMat *dP0 = nullptr, *dS = nullptr;
+  if (gpu && dA && dP_out) {  // device chain: only P0, the weights (and a filtered A_F) go up, only P comes down
+    GpuMat *dP0 = nullptr, *dF = nullptr, *dP = nullptr;
+    bool ok = false;
     try {
+      std::vector<double> w(n);
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) w[i] = -(omega * dinv[i]);
       dP0 = gpu_upload(P0);
-      dS = gpu_product(dA, dP0);
-      gpu_download(dS, S);
-      done = true;
+      if (F != &A) dF = gpu_upload(*F);
+      dP = gpu_smooth_prolongator(dF ? dF : dA, dP0, w.data());
+      gpu_download(dP, P);
+      ok = true;
     } catch (const std::exception& e) {
-      std::fprintf(stderr, "[pamg setup] GPU product failed (%s): falling back to the host\n", e.what());
+      std::fprintf(stderr, "[pamg setup] GPU prolongator smoothing failed (%s): falling back to the host\n", e.what());
+      gpu_free(dP);
+      dP = nullptr;
     }
     gpu_free(dP0);
-    gpu_free(dS);
+    gpu_free(dF);
+    if (ok) {
+      *dP_out = dP;
+      return;
+    }
   }
-  if (!done) product(*F, P0, S, gpu);
+  Csr S;
+  product(*F, P0, S, gpu);
   P.nrows = n;
   P.ncols = nc;
   P.ptr.assign(n + 1, 0);
@@ -1021,10 +1033,15 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
   PhaseTimer tm;
   bool gpu = gpu_setup_available();  // the three sparse products of every level run on the GPU when one is there
   GpuMat* dA = nullptr;              // device copy of the current level's matrix (GPU chain)
-  struct DaGuard {                   // an exception below must not leak device memory
+  struct DaGuard {                   // an exception below must not leak device memory or pinned staging
     GpuMat*& p;
-    ~DaGuard() { gpu_free(p); }
-  } da_guard{dA};
+    bool staging;
+    ~DaGuard() {
+      gpu_free(p);
+      if (staging) gpu_setup_end();
+    }
+  } da_guard{dA, gpu};
+  if (gpu) gpu_setup_begin();
   if (tm.on) std::fprintf(stderr, "[pamg setup] sparse products on the %s\n", gpu ? "GPU" : "host");
   if (A0.nrows != (int64_t)owner0.size()) throw std::runtime_error("owner size mismatch");
   const bool use_ns = nullspace && ns_k > 0;
@@ -1149,20 +1166,31 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       tentative_from_nullspace(Bcur, kdof, bs, agg_node, nagg, P0, Bc, dead);
     }
     tm.lap("aggregation + P0", (int)g.size() - 1);
-    build_prolongator(cur.A(), P0, nc, eps, absdiag, cur.P, &cur.omega_p, gpu, dA);
-    tm.lap("prolongator smoothing", (int)g.size() - 1);
-    transpose(cur.P, cur.R);
-    tm.lap("transpose", (int)g.size() - 1);
+    GpuMat *dP = nullptr, *dR = nullptr;  // resident copies of P and R (GPU chain)
+    build_prolongator(cur.A(), P0, nc, eps, absdiag, cur.P, &cur.omega_p, gpu, dA, &dP);
+    tm.lap(dP ? "prolongator smoothing (GPU)" : "prolongator smoothing", (int)g.size() - 1);
+    if (dP) {
+      try {
+        dR = gpu_transpose(dP);
+        gpu_download(dR, cur.R);
+      } catch (const std::exception& e) {
+        std::fprintf(stderr, "[pamg setup] GPU transpose failed (%s): falling back to the host\n", e.what());
+        gpu_free(dR);
+        dR = nullptr;
+      }
+    }
+    if (!dR) transpose(cur.P, cur.R);
+    tm.lap(dR ? "transpose (GPU)" : "transpose", (int)g.size() - 1);
     G nxt;
     bool galerkin_done = false;
     GpuMat* dAc = nullptr;
-    if (gpu && dA) {  // A is resident: A*P stays on the device, only P, R go up and A_c comes down
-      GpuMat *dP = nullptr, *dR = nullptr, *dAP = nullptr;
+    if (gpu && dA) {  // A (and usually P, R) resident: A*P stays on the device, only A_c comes down
+      GpuMat* dAP = nullptr;
       try {
-        dP = gpu_upload(cur.P);
+        if (!dP) dP = gpu_upload(cur.P);
         dAP = gpu_product(dA, dP);
         tm.lap("A*P (GPU)", (int)g.size() - 1);
-        dR = gpu_upload(cur.R);
+        if (!dR) dR = gpu_upload(cur.R);
         dAc = gpu_product(dR, dAP);
         gpu_download(dAc, nxt.A_own);
         tm.lap("R*(AP) (GPU)", (int)g.size() - 1);
@@ -1172,10 +1200,10 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
         gpu_free(dAc);
         dAc = nullptr;
       }
-      gpu_free(dP);
-      gpu_free(dR);
       gpu_free(dAP);
     }
+    gpu_free(dP);
+    gpu_free(dR);
     gpu_free(dA);  // the fine matrix is not needed on the device any more
     dA = nullptr;
     if (!galerkin_done) {

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -52,11 +53,94 @@ struct Buf {
     GK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
     n = count;
   }
-  void upload(const T* h, size_t count) {
-    alloc(count);
-    if (count) GK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  void upload(const T* h, size_t count);
+  void download(T* h, size_t count) const;
+};
+
+// Host arrays of the setup are pageable std::vectors (a few GB at 256^3): a plain cudaMemcpy moves them at 3-4 GB/s.
+// Staged through two pinned 64 MB buffers (parallel memcpy into one while the DMA drains the other) they move at PCIe speed.
+struct Staging {
+  static constexpr size_t BYTES = (size_t)64 << 20;
+  char* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t st = nullptr;
+  bool ok = false;
+  Staging() {
+    if (cudaHostAlloc((void**)&buf[0], BYTES, cudaHostAllocDefault) != cudaSuccess) return;
+    if (cudaHostAlloc((void**)&buf[1], BYTES, cudaHostAllocDefault) != cudaSuccess) return;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) return;
+    ok = true;
+  }
+  ~Staging() {
+    for (int k = 0; k < 2; ++k) {
+      if (ev[k]) cudaEventDestroy(ev[k]);
+      if (buf[k]) cudaFreeHost(buf[k]);
+    }
+    if (st) cudaStreamDestroy(st);
   }
 };
+Staging*& staging_slot() {
+  static Staging* s = nullptr;
+  return s;
+}
+void par_copy(char* dst, const char* src, size_t bytes) {
+  const int64_t nb = (int64_t)((bytes + 4095) / 4096);
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < nb; ++b) {
+    const size_t o = (size_t)b * 4096;
+    std::memcpy(dst + o, src + o, std::min<size_t>(4096, bytes - o));
+  }
+}
+void staged_h2d(void* dev, const void* host, size_t bytes) {
+  Staging* S = staging_slot();
+  if (!S || !S->ok || bytes < ((size_t)8 << 20)) {
+    GK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+    return;
+  }
+  GK(cudaDeviceSynchronize());  // the device buffer may have been produced on the default stream
+  int k = 0;
+  for (size_t o = 0; o < bytes; o += Staging::BYTES, k ^= 1) {
+    const size_t m = std::min(Staging::BYTES, bytes - o);
+    GK(cudaEventSynchronize(S->ev[k]));  // the DMA that last used this buffer is done
+    par_copy(S->buf[k], (const char*)host + o, m);
+    GK(cudaMemcpyAsync((char*)dev + o, S->buf[k], m, cudaMemcpyHostToDevice, S->st));
+    GK(cudaEventRecord(S->ev[k], S->st));
+  }
+  GK(cudaStreamSynchronize(S->st));
+}
+void staged_d2h(void* host, const void* dev, size_t bytes) {
+  Staging* S = staging_slot();
+  if (!S || !S->ok || bytes < ((size_t)8 << 20)) {
+    GK(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+    return;
+  }
+  GK(cudaDeviceSynchronize());
+  // chunk c is copied device -> pinned[c & 1] while chunk c - 1 is copied pinned -> pageable on the host
+  const size_t nchunks = (bytes + Staging::BYTES - 1) / Staging::BYTES;
+  for (size_t c = 0; c <= nchunks; ++c) {
+    if (c < nchunks) {
+      const size_t o = c * Staging::BYTES, m = std::min(Staging::BYTES, bytes - o);
+      GK(cudaMemcpyAsync(S->buf[c & 1], (const char*)dev + o, m, cudaMemcpyDeviceToHost, S->st));
+      GK(cudaEventRecord(S->ev[c & 1], S->st));
+    }
+    if (c > 0) {
+      const size_t o = (c - 1) * Staging::BYTES, m = std::min(Staging::BYTES, bytes - o);
+      GK(cudaEventSynchronize(S->ev[(c - 1) & 1]));
+      par_copy((char*)host + o, S->buf[(c - 1) & 1], m);
+    }
+  }
+}
+template <class T>
+void Buf<T>::upload(const T* h, size_t count) {
+  alloc(count);
+  if (count) staged_h2d(p, h, count * sizeof(T));
+}
+template <class T>
+void Buf<T>::download(T* h, size_t count) const {
+  if (count) staged_d2h(h, p, count * sizeof(T));
+}
 
 constexpr int TB = 256;
 
@@ -124,6 +208,14 @@ int bits_for(uint64_t v) {
 
 }  // namespace
 
+void gpu_setup_begin() {
+  if (!staging_slot()) staging_slot() = new Staging;
+}
+void gpu_setup_end() {
+  delete staging_slot();
+  staging_slot() = nullptr;
+}
+
 bool gpu_setup_available() {
   // opt-in: with the host CSR in int64 / pageable memory the PCIe marshalling eats what the device products save
   // (256^3: 10.4 s with the GPU chain vs 9.5 s on 16 host cores, profiles/r02_setup_timing.txt)
@@ -167,10 +259,10 @@ void gpu_download(const GpuMat* m, Csr& C) {
   C.col.resize(m->nnz);
   C.val.resize(m->nnz);
   std::vector<int32_t> col32(m->nnz);
-  GK(cudaMemcpy(C.ptr.data(), m->ptr.p, (m->nrows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  m->ptr.download(C.ptr.data(), (size_t)m->nrows + 1);
   if (m->nnz) {
-    GK(cudaMemcpy(col32.data(), m->col.p, m->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    GK(cudaMemcpy(C.val.data(), m->val.p, m->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    m->col.download(col32.data(), (size_t)m->nnz);
+    m->val.download(C.val.data(), (size_t)m->nnz);
   }
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < m->nnz; ++k) C.col[k] = col32[k];
@@ -299,6 +391,132 @@ GpuMat* gpu_product(const GpuMat* A, const GpuMat* B) {
   }
   GK(cudaDeviceSynchronize());
   return C.release();
+}
+
+// ---- prolongator smoothing on the device: P = P0 - omega D^-1 S, S = A_F P0, merged by column (host_setup.cpp build_prolongator)
+__global__ void k_merge_count(const int64_t* __restrict__ s_ptr, const int32_t* __restrict__ s_col, const int64_t* __restrict__ p_ptr,
+                              const int32_t* __restrict__ p_col, int64_t n, int64_t* __restrict__ cnt) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  int64_t pk = p_ptr[i], c = 0;
+  const int64_t pe = p_ptr[i + 1];
+  for (int64_t k = s_ptr[i]; k < s_ptr[i + 1]; ++k) {
+    const int32_t col = s_col[k];
+    while (pk < pe && p_col[pk] < col) {
+      ++pk;
+      ++c;
+    }
+    if (pk < pe && p_col[pk] == col) ++pk;
+    ++c;
+  }
+  cnt[i] = c + (pe - pk);
+}
+__global__ void k_merge_fill(const int64_t* __restrict__ s_ptr, const int32_t* __restrict__ s_col, const double* __restrict__ s_val,
+                             const int64_t* __restrict__ p_ptr, const int32_t* __restrict__ p_col, const double* __restrict__ p_val,
+                             const double* __restrict__ w, int64_t n, const int64_t* __restrict__ o_ptr, int32_t* __restrict__ o_col,
+                             double* __restrict__ o_val) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  int64_t pk = p_ptr[i], q = o_ptr[i];
+  const int64_t pe = p_ptr[i + 1];
+  const double wi = w[i];
+  for (int64_t k = s_ptr[i]; k < s_ptr[i + 1]; ++k) {
+    const int32_t col = s_col[k];
+    while (pk < pe && p_col[pk] < col) {
+      o_col[q] = p_col[pk];
+      o_val[q++] = p_val[pk++];
+    }
+    double v = __dmul_rn(wi, s_val[k]);  // rounded product, then a rounded add: the host's arithmetic, no FMA
+    if (pk < pe && p_col[pk] == col) v = __dadd_rn(p_val[pk++], v);
+    o_col[q] = col;
+    o_val[q++] = v;
+  }
+  while (pk < pe) {
+    o_col[q] = p_col[pk];
+    o_val[q++] = p_val[pk++];
+  }
+}
+
+void exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, Buf<char>& tmp) {
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n);
+  tmp.alloc(need);
+  size_t tb = tmp.n;
+  GK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n));
+}
+
+// P = P0 + diag(w) (F P0) with w_i = -(omega / d_F,i); F and P0 resident, w from the host
+GpuMat* gpu_smooth_prolongator(const GpuMat* F, const GpuMat* P0, const double* w_host) {
+  std::unique_ptr<GpuMat> S(gpu_product(F, P0));
+  const int64_t n = F->nrows;
+  std::unique_ptr<GpuMat> P(new GpuMat);
+  P->nrows = n;
+  P->ncols = P0->ncols;
+  Buf<double> d_w;
+  d_w.upload(w_host, (size_t)n);
+  Buf<int64_t> d_cnt;
+  Buf<char> tmp;
+  d_cnt.alloc(n + 1);
+  GK(cudaMemset(d_cnt.p, 0, (n + 1) * sizeof(int64_t)));
+  const int g = (int)((n + TB - 1) / TB);
+  if (n) k_merge_count<<<g, TB>>>(S->ptr.p, S->col.p, P0->ptr.p, P0->col.p, n, d_cnt.p);
+  P->ptr.alloc(n + 1);
+  exclusive_scan_i64(d_cnt.p, P->ptr.p, n + 1, tmp);
+  GK(cudaMemcpy(&P->nnz, P->ptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  P->col.alloc(P->nnz);
+  P->val.alloc(P->nnz);
+  if (n) k_merge_fill<<<g, TB>>>(S->ptr.p, S->col.p, S->val.p, P0->ptr.p, P0->col.p, P0->val.p, d_w.p, n, P->ptr.p, P->col.p, P->val.p);
+  GK(cudaGetLastError());
+  GK(cudaDeviceSynchronize());
+  return P.release();
+}
+
+// ---- R = P^T on the device: keys (column << 32 | row) are unique, so sorting them IS the transpose with ascending columns
+__global__ void k_tr_keys(const int64_t* __restrict__ ptr, const int32_t* __restrict__ col, int64_t n, unsigned long long* __restrict__ keys,
+                          unsigned long long* __restrict__ col_cnt) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) {
+    keys[k] = ((unsigned long long)(uint32_t)col[k] << 32) | (unsigned long long)(uint32_t)i;
+    atomicAdd(col_cnt + col[k], 1ull);
+  }
+}
+__global__ void k_tr_unpack(const unsigned long long* __restrict__ keys, int64_t nnz, int32_t* __restrict__ out_col) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i < nnz) out_col[i] = (int32_t)(uint32_t)(keys[i] & 0xffffffffull);
+}
+GpuMat* gpu_transpose(const GpuMat* A) {
+  std::unique_ptr<GpuMat> T(new GpuMat);
+  T->nrows = A->ncols;
+  T->ncols = A->nrows;
+  T->nnz = A->nnz;
+  const int64_t n = A->nrows, nc = A->ncols, nnz = A->nnz;
+  Buf<unsigned long long> keys, keys2, cnt;
+  Buf<int64_t> cnt64;
+  Buf<char> tmp;
+  keys.alloc(nnz);
+  keys2.alloc(nnz);
+  cnt.alloc(nc + 1);
+  GK(cudaMemset(cnt.p, 0, (nc + 1) * sizeof(unsigned long long)));
+  if (n) k_tr_keys<<<(int)((n + TB - 1) / TB), TB>>>(A->ptr.p, A->col.p, n, keys.p, cnt.p);
+  T->val.alloc(nnz);
+  T->col.alloc(nnz);
+  if (nnz) {
+    size_t need = 0;
+    const int end_bit = 32 + bits_for((uint64_t)std::max<int64_t>(nc - 1, 1));
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys.p, keys2.p, A->val.p, T->val.p, nnz, 0, end_bit);
+    tmp.alloc(need);
+    size_t tb = tmp.n;
+    GK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys2.p, A->val.p, T->val.p, nnz, 0, end_bit));
+    k_tr_unpack<<<(int)((nnz + TB - 1) / TB), TB>>>(keys2.p, nnz, T->col.p);
+  }
+  cnt64.alloc(nc + 1);
+  k_set_u64_to_i64<<<(int)((nc + 1 + TB - 1) / TB), TB>>>(cnt.p, nc + 1, cnt64.p);
+  T->ptr.alloc(nc + 1);
+  exclusive_scan_i64(cnt64.p, T->ptr.p, nc + 1, tmp);
+  GK(cudaGetLastError());
+  GK(cudaDeviceSynchronize());
+  return T.release();
 }
 
 void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
