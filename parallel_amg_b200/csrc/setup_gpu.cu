@@ -217,10 +217,10 @@ void gpu_setup_end() {
 }
 
 bool gpu_setup_available() {
-  // opt-in: with the host CSR in int64 / pageable memory the PCIe marshalling eats what the device products save
-  // (256^3: 10.4 s with the GPU chain vs 9.5 s on 16 host cores, profiles/r02_setup_timing.txt)
+  // on whenever a device is there (PAMG_GPU_SETUP=0: host products).  256^3 on the GPU box: 6.1 s with the device chain
+  // (smoothing, transpose, A*P, R*(AP) resident; pinned staging) vs 9.6 s on 16 host cores, profiles/r02_setup_timing.txt
   const char* e = getenv("PAMG_GPU_SETUP");
-  if (!e || atoi(e) == 0) return false;
+  if (e && atoi(e) == 0) return false;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
     cudaGetLastError();
