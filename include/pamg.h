@@ -252,6 +252,14 @@ int pamg_pcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol,
 int pamg_fcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter, int32_t* iters,
              double* resid_hist);
 
+/* Restarted flexible GMRES, FGMRES(restart), right-preconditioned by one multigrid cycle (precond = 0: plain restarted
+ * GMRES), from x = 0: Arnoldi with modified Gram-Schmidt on w = A M^-1 v_j, Givens rotations; resid_hist[0] = ||b||,
+ * resid_hist[k] = the residual estimate |g_k| after inner step k (capacity maxiter + 1); stops at estimate <= rtol ||b|| or
+ * after maxiter inner steps.  For operators or cycles that are not symmetric (PartitionedSolvers / IterativeSolvers `gmres`
+ * [RECALL-UNVERIFIED]); oracle: amg_oracle.py fgmres / pamg_oracle.c orc_fgmres.  Device memory: (2 restart + 1) vectors. */
+int pamg_fgmres(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter, int32_t restart,
+                int32_t precond, int32_t* iters, double* resid_hist);
+
 /* ---- device-resident benchmarking hooks (inputs already in HBM) ------------------------
  * pamg_load_rhs copies b to the device once; pamg_pcg_resident re-solves from x=0 with the
  * resident b and leaves x on the device (pamg_read_solution fetches it). */

@@ -927,6 +927,71 @@ def pcg(h, bs, rtol=1e-8, maxiter=200, precond=True, flexible=False):
     return xs, it, hist
 
 
+def fgmres(h, bs, rtol=1e-8, maxiter=200, restart=30, precond=True):
+    """Restarted flexible GMRES (Saad, FGMRES(m)), right-preconditioned by one multigrid cycle, x0 = 0:
+    Arnoldi with modified Gram-Schmidt on w = A M^-1 v_j, Givens rotations on the Hessenberg columns, the residual
+    estimate |g_{j+1}| recorded per inner step (hist[0] = ||b||), stop at estimate <= rtol * ||b|| or maxiter inner
+    steps; x += sum_j y_j z_j with the stored z_j = M^-1 v_j; after a restart r = b - A x is recomputed.
+    Returns xs, inner iterations, hist."""
+    level = h["levels"][0]
+    n_own = [len(d["own_to_global"]) for d in level["parts"]]
+    own = lambda vs: [v[:n].copy() for v, n in zip(vs, n_own)]                      # noqa: E731
+    pad = lambda vs: [np.concatenate([v, np.zeros(len(d["ghost_to_global"]))]) for v, d in zip(vs, level["parts"])]  # noqa: E731
+    M = (lambda v: own(vcycle(h, pad(v)))) if precond else (lambda v: [a.copy() for a in v])
+    dot = lambda us, vs: pdot(level, pad(us), pad(vs))                              # noqa: E731
+    xs = [np.zeros(n) for n in n_own]
+    rs = own(bs)
+    beta0 = np.sqrt(dot(rs, rs))
+    hist = [beta0]
+    it = 0
+    if beta0 == 0.0 or maxiter == 0:
+        return pad(xs), 0, hist
+    done = False
+    while not done:
+        beta = np.sqrt(dot(rs, rs))
+        V = [[r / beta for r in rs]]
+        Z = []
+        H = np.zeros((restart + 1, restart))
+        cs, sn = np.zeros(restart), np.zeros(restart)
+        g = np.zeros(restart + 1)
+        g[0] = beta
+        j = 0
+        while j < restart:
+            z = M(V[j])
+            Z.append(z)
+            w = own(spmv(level, pad(z)))
+            for i in range(j + 1):
+                H[i, j] = dot(w, V[i])
+                w = [a - H[i, j] * v for a, v in zip(w, V[i])]
+            H[j + 1, j] = np.sqrt(dot(w, w))
+            V.append([a / H[j + 1, j] for a in w] if H[j + 1, j] != 0.0 else [a.copy() for a in w])
+            for i in range(j):   # previous rotations on the new column
+                t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+                H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+                H[i, j] = t
+            d = np.hypot(H[j, j], H[j + 1, j])
+            cs[j], sn[j] = H[j, j] / d, H[j + 1, j] / d
+            H[j, j] = d
+            H[j + 1, j] = 0.0
+            g[j + 1] = -sn[j] * g[j]
+            g[j] = cs[j] * g[j]
+            j += 1
+            it += 1
+            hist.append(abs(g[j]))
+            if abs(g[j]) <= rtol * beta0 or it >= maxiter:
+                done = True
+                break
+        y = np.zeros(j)
+        for i in range(j - 1, -1, -1):   # back substitution
+            y[i] = (g[i] - H[i, i + 1:j] @ y[i + 1:j]) / H[i, i]
+        for i in range(j):
+            xs = [x + y[i] * z for x, z in zip(xs, Z[i])]
+        if not done:
+            ax = own(spmv(level, pad(xs)))
+            rs = [b[:n] - a for b, a, n in zip(bs, ax, n_own)]
+    return pad(xs), it, hist
+
+
 # --------------------------------------------------------------------------------------
 # convenience: everything for one problem
 # --------------------------------------------------------------------------------------

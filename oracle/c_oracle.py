@@ -47,6 +47,8 @@ def _load():
     lib.orc_vcycle.argtypes = [C.c_void_p, C.POINTER(_f64p), C.POINTER(_f64p)]
     lib.orc_pcg.restype = C.c_int32
     lib.orc_pcg.argtypes = [C.c_void_p, C.POINTER(_f64p), C.POINTER(_f64p), C.c_double, C.c_int32, C.c_int32, _f64p]
+    lib.orc_fgmres.restype = C.c_int32
+    lib.orc_fgmres.argtypes = [C.c_void_p, C.POINTER(_f64p), C.POINTER(_f64p), C.c_double, C.c_int32, C.c_int32, C.c_int32, _f64p]
     return lib
 
 
@@ -161,6 +163,14 @@ class COracle:
         hist = np.zeros(maxiter + 2)
         mode = 2 if (flexible and precond) else int(bool(precond))
         it = self.lib.orc_pcg(self.h, bp, xp, float(rtol), int(maxiter), mode, _p(hist, C.c_double))
+        return k2, int(it), hist[: it + 1].copy()
+
+    def fgmres(self, b_parts, rtol=1e-8, maxiter=200, restart=30, precond=True):
+        x = [np.zeros(n) for n in self.n_own[0]]
+        bp, k1 = self._vecs(b_parts)
+        xp, k2 = self._vecs(x)
+        hist = np.zeros(maxiter + 2)
+        it = self.lib.orc_fgmres(self.h, bp, xp, float(rtol), int(maxiter), int(restart), int(bool(precond)), _p(hist, C.c_double))
         return k2, int(it), hist[: it + 1].copy()
 
     def close(self):

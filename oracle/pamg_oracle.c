@@ -11,6 +11,7 @@
  *   orc_jacobi       <- amg_oracle.jacobi_sweep    (damped / l1 Jacobi; w passed in)
  *   orc_vcycle       <- amg_oracle.vcycle
  *   orc_pcg          <- amg_oracle.pcg
+ *   orc_fgmres       <- amg_oracle.fgmres          (restarted flexible GMRES, right-preconditioned)
  * It is checked against amg_oracle.py in tests/test_c_oracle.py (<= 1e-12, same iteration counts).
  *
  * Execution model: PartitionedArrays debug backend — all parts in one process, each part reads
@@ -358,5 +359,135 @@ int32_t orc_pcg(orc_t* o, const double* const* b_parts, double* const* x_parts, 
     free(zs[q]);
     free(ro[q]);
   }
+  return it;
+}
+
+/* Restarted flexible GMRES, FGMRES(m), right-preconditioned by one cycle, x0 = 0 (amg_oracle.fgmres): Arnoldi with
+ * modified Gram-Schmidt on w = A M^-1 v_j, Givens rotations, hist[k] = |g_{k}| (the residual estimate of inner step k,
+ * hist[0] = ||b||); stops at estimate <= rtol ||b|| or maxiter inner steps.  Returns the inner iterations. */
+int32_t orc_fgmres(orc_t* o, const double* const* b_parts, double* const* x_parts, double rtol, int32_t maxiter,
+                   int32_t restart, int32_t precond, double* hist) {
+  const int P = o->nparts, m = restart;
+  double** V = (double**)calloc((size_t)(m + 1) * P, sizeof(double*)); /* V[j*P + q] */
+  double** Z = (double**)calloc((size_t)m * P, sizeof(double*));
+  double *xs[256], *rs[256], *ws[256];
+  for (int q = 0; q < P; ++q) {
+    part_t* p = &PART(o, 0, q);
+    size_t nl = (size_t)(p->n_own + p->n_ghost) + 1;
+    xs[q] = (double*)calloc(nl, sizeof(double));
+    rs[q] = (double*)calloc(nl, sizeof(double));
+    ws[q] = (double*)calloc(nl, sizeof(double));
+    memcpy(rs[q], b_parts[q], sizeof(double) * (size_t)p->n_own);
+    for (int j = 0; j <= m; ++j) V[(size_t)j * P + q] = (double*)calloc(nl, sizeof(double));
+    for (int j = 0; j < m; ++j) Z[(size_t)j * P + q] = (double*)calloc(nl, sizeof(double));
+  }
+  double* H = (double*)calloc((size_t)(m + 1) * m, sizeof(double)); /* H[i*m + j] */
+  double* cs = (double*)calloc(m, sizeof(double));
+  double* sn = (double*)calloc(m, sizeof(double));
+  double* g = (double*)calloc(m + 1, sizeof(double));
+  double* y = (double*)calloc(m, sizeof(double));
+  const double beta0 = sqrt(pdot(o, rs, rs));
+  if (hist) hist[0] = beta0;
+  int32_t it = 0;
+  int done = (beta0 == 0.0 || maxiter == 0);
+  while (!done) {
+    const double beta = sqrt(pdot(o, rs, rs));
+    for (int q = 0; q < P; ++q) {
+      const int64_t n = PART(o, 0, q).n_own;
+      double* v = V[q];
+      const double* r = rs[q];
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) v[i] = r[i] / beta;
+    }
+    memset(H, 0, sizeof(double) * (size_t)(m + 1) * m);
+    memset(g, 0, sizeof(double) * (size_t)(m + 1));
+    g[0] = beta;
+    int j = 0;
+    while (j < m) {
+      double** vj = V + (size_t)j * P;
+      double** zj = Z + (size_t)j * P;
+      if (precond) {
+        for (int q = 0; q < P; ++q) memcpy(PART(o, 0, q).b_, vj[q], sizeof(double) * (size_t)PART(o, 0, q).n_own);
+        vcycle(o, 0);
+        for (int q = 0; q < P; ++q) memcpy(zj[q], PART(o, 0, q).x, sizeof(double) * (size_t)PART(o, 0, q).n_own);
+      } else {
+        for (int q = 0; q < P; ++q) memcpy(zj[q], vj[q], sizeof(double) * (size_t)PART(o, 0, q).n_own);
+      }
+      orc_spmv(o, 0, zj, ws);
+      for (int i = 0; i <= j; ++i) {
+        double** vi = V + (size_t)i * P;
+        const double h = pdot(o, ws, vi);
+        H[(size_t)i * m + j] = h;
+        for (int q = 0; q < P; ++q) {
+          const int64_t n = PART(o, 0, q).n_own;
+          double* w = ws[q];
+          const double* v = vi[q];
+#pragma omp parallel for schedule(static)
+          for (int64_t k = 0; k < n; ++k) w[k] = w[k] - h * v[k];
+        }
+      }
+      const double hn = sqrt(pdot(o, ws, ws));
+      H[(size_t)(j + 1) * m + j] = hn;
+      for (int q = 0; q < P; ++q) {
+        const int64_t n = PART(o, 0, q).n_own;
+        double* v = V[(size_t)(j + 1) * P + q];
+        const double* w = ws[q];
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < n; ++k) v[k] = hn != 0.0 ? w[k] / hn : w[k];
+      }
+      for (int i = 0; i < j; ++i) { /* previous rotations on the new column */
+        const double t = cs[i] * H[(size_t)i * m + j] + sn[i] * H[(size_t)(i + 1) * m + j];
+        H[(size_t)(i + 1) * m + j] = -sn[i] * H[(size_t)i * m + j] + cs[i] * H[(size_t)(i + 1) * m + j];
+        H[(size_t)i * m + j] = t;
+      }
+      const double d = hypot(H[(size_t)j * m + j], H[(size_t)(j + 1) * m + j]);
+      cs[j] = H[(size_t)j * m + j] / d;
+      sn[j] = H[(size_t)(j + 1) * m + j] / d;
+      H[(size_t)j * m + j] = d;
+      H[(size_t)(j + 1) * m + j] = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      ++j;
+      ++it;
+      if (hist) hist[it] = fabs(g[j]);
+      if (fabs(g[j]) <= rtol * beta0 || it >= maxiter) {
+        done = 1;
+        break;
+      }
+    }
+    for (int i = j - 1; i >= 0; --i) { /* back substitution, the dot in ascending column order */
+      double s = 0.0;
+      for (int k = i + 1; k < j; ++k) s += H[(size_t)i * m + k] * y[k];
+      y[i] = (g[i] - s) / H[(size_t)i * m + i];
+    }
+    for (int i = 0; i < j; ++i)
+      for (int q = 0; q < P; ++q) {
+        const int64_t n = PART(o, 0, q).n_own;
+        double* x = xs[q];
+        const double* z = Z[(size_t)i * P + q];
+        const double yi = y[i];
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < n; ++k) x[k] = x[k] + yi * z[k];
+      }
+    if (!done) {
+      orc_spmv(o, 0, xs, ws);
+      for (int q = 0; q < P; ++q) {
+        const int64_t n = PART(o, 0, q).n_own;
+        double* r = rs[q];
+        const double *b = b_parts[q], *a = ws[q];
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < n; ++k) r[k] = b[k] - a[k];
+      }
+    }
+  }
+  for (int q = 0; q < P; ++q) {
+    memcpy(x_parts[q], xs[q], sizeof(double) * (size_t)PART(o, 0, q).n_own);
+    free(xs[q]);
+    free(rs[q]);
+    free(ws[q]);
+    for (int j = 0; j <= m; ++j) free(V[(size_t)j * P + q]);
+    for (int j = 0; j < m; ++j) free(Z[(size_t)j * P + q]);
+  }
+  free(V); free(Z); free(H); free(cs); free(sn); free(g); free(y);
   return it;
 }

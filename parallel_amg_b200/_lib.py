@@ -110,6 +110,7 @@ PROTOTYPES = {
     "pamg_vcycle": [_ctx, _vecs, _vecs],
     "pamg_pcg": [_ctx, _vecs, _vecs, C.c_double, C.c_int32, C.c_int32, _i32p, _f64p],
     "pamg_fcg": [_ctx, _vecs, _vecs, C.c_double, C.c_int32, _i32p, _f64p],
+    "pamg_fgmres": [_ctx, _vecs, _vecs, C.c_double, C.c_int32, C.c_int32, C.c_int32, _i32p, _f64p],
     "pamg_load_rhs": [_ctx, _vecs],
     "pamg_pcg_resident": [_ctx, C.c_double, C.c_int32, C.c_int32, _i32p, _f64p],
     "pamg_read_solution": [_ctx, _vecs],
@@ -512,6 +513,17 @@ class Context:
         hist = np.zeros(maxiter + 2)
         st = self._ck(self.lib.pamg_fcg(self._h, bp, xp, float(rtol), int(maxiter), C.byref(it), _ptr(hist, C.c_double)),
                       allow=(ERR_NOTCONV,))
+        return x, it.value, hist[:it.value + 1].copy(), st == OK
+
+    def fgmres(self, b, rtol=1e-8, maxiter=200, restart=30, precond=True, out=None):
+        """restarted flexible GMRES right-preconditioned by one cycle; same results tuple as pcg() (hist = residual estimates)."""
+        x = out if out is not None else self._new_own(0)
+        bp, k1 = self._vecs(b)
+        xp, k2 = self._vecs(x, writable=True)
+        it = C.c_int32()
+        hist = np.zeros(maxiter + 2)
+        st = self._ck(self.lib.pamg_fgmres(self._h, bp, xp, float(rtol), int(maxiter), int(restart), int(bool(precond)),
+                                           C.byref(it), _ptr(hist, C.c_double)), allow=(ERR_NOTCONV,))
         return x, it.value, hist[:it.value + 1].copy(), st == OK
 
     def load_rhs(self, b):

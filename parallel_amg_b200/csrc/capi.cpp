@@ -759,6 +759,13 @@ int pamg_fcg(pamg_ctx* c, const double* const* b, double* const* x, double rtol,
     return engine(c).pcg(b, x, rtol, maxiter, 2, iters, resid_hist);
   });
 }
+int pamg_fgmres(pamg_ctx* c, const double* const* b, double* const* x, double rtol, int32_t maxiter, int32_t restart,
+                int32_t precond, int32_t* iters, double* resid_hist) {
+  return guard(c, [&] {
+    need(b && x && rtol >= 0.0 && maxiter >= 0 && restart >= 1, "bad arguments");
+    return engine(c).fgmres(b, x, rtol, maxiter, restart, precond, iters, resid_hist);
+  });
+}
 int pamg_load_rhs(pamg_ctx* c, const double* const* b) {
   return guard(c, [&] {
     need(b != nullptr, "null vectors");

@@ -457,6 +457,10 @@ struct PartDev {
   DBuf<int64_t> own_gid_T, ghost_gid_T;
   DBuf<double> xsol, p, q, bsave, hist, scratch4, rprev;  // rprev: r_k of flexible CG (allocated on first use)
   DBuf<double> io_local;  // own+ghost staging for consistent!/assemble!
+  DBuf<double> gm_basis;  // FGMRES: V_0..V_m then Z_0..Z_{m-1}, own length each (allocated on first use)
+  DBuf<double> gm_h;      // FGMRES: one Hessenberg column (m + 2 doubles), written by k_gs_sub / k_gs_norm
+  int gm_restart = 0;
+  bool gm_precond = false;
   DBuf<unsigned long long> trace;
   std::vector<Renumbering> renum;  // per level: device numbering of the own rows (identity on level 0)
   DBuf<TailOp> tail_ops;           // phases of the fused replicated tail (k_tail_fused), empty: multi-launch tail
@@ -2261,6 +2265,221 @@ int Engine::pcg_resident(double rtol, int maxiter, int mode, int* iters, double*
   I.stats.converged = conv;
   I.stats.r0_norm = r0;
   I.stats.r_norm = rn;
+  I.stats.solve_ms = mx;
+  I.stats.kernel_launches = I.launches;
+  return conv ? PAMG_OK : PAMG_ERR_NOTCONV;
+}
+
+// ---------------------------------------------------------------------------------------------
+// restarted flexible GMRES (oracle/amg_oracle.py fgmres, pamg_oracle.c orc_fgmres)
+// ---------------------------------------------------------------------------------------------
+// Host-driven: the cycle (one graph replay), the SpMV (fused halo roles as in PCG) and the modified Gram-Schmidt chain
+// (k_dot -> k_gs_sub pairs: the coefficient goes from the all-reduce straight into the update) are enqueued per inner
+// step; one Hessenberg column comes back per step for the Givens rotations, the residual estimate and the stopping
+// decision.  Every part reads bit-identical all-reduce results, so every rank of a one-process-per-GPU job takes the
+// same decisions without talking to the others.
+int Engine::fgmres(const double* const* b, double* const* x, double rtol, int maxiter, int restart, int precond, int* iters,
+                   double* hist) {
+  require_connected();
+  Impl& I = *impl;
+  if (maxiter < 0) throw std::runtime_error("maxiter < 0");
+  if (restart < 1 || restart > 1000) throw std::runtime_error("restart must be in [1, 1000]");
+  const int m = restart;
+  const bool pre = precond != 0;
+  const size_t np = I.parts.size();
+  load_rhs(b);
+  I.launches = 0;
+  std::vector<size_t> stride(np);
+  for (size_t i = 0; i < np; ++i) {
+    PartDev& pd = I.P(i);
+    I.set_dev(pd);
+    stride[i] = align_up((size_t)pd.lev[0]->n_own, 32);
+    if (pd.gm_restart != m || pd.gm_precond != pre || pd.gm_basis.n == 0) {
+      pd.gm_basis.alloc(stride[i] * (size_t)(pre ? 2 * m + 1 : m + 1), false);
+      pd.gm_h.alloc((size_t)m + 2);
+      pd.gm_restart = m;
+      pd.gm_precond = pre;
+    }
+  }
+  auto V = [&](size_t i, int j) { return I.P(i).gm_basis.p + stride[i] * (size_t)j; };
+  auto Z = [&](size_t i, int j) { return pre ? I.P(i).gm_basis.p + stride[i] * (size_t)(m + 1 + j) : V(i, j); };
+  const bool use_graph = I.h->opts.use_graph != 0;
+  if (pre && use_graph && I.g_vcycle.empty()) capture(I.g_vcycle, &I.g_vcycle_nodes, [&] { enqueue_vcycle_entry(); });
+  clear_done();
+  // <u, v> over all parts, returned to the host (one synchronisation)
+  auto host_dot = [&](auto&& uf, auto&& vf) {
+    for (size_t i = 0; i < np; ++i) {
+      PartDev& pd = I.P(i);
+      I.set_dev(pd);
+      const int n = (int)pd.lev[0]->n_own;
+      k_dot<<<I.grid_red(n), BLOCK, 0, pd.stream>>>(uf(i), vf(i), n, pd.st.p, pd.partials.p, pd.rc, 3, 0);
+      I.note_launch("k_dot");
+    }
+    for (size_t i = 0; i < np; ++i) {
+      PartDev& pd = I.P(i);
+      I.set_dev(pd);
+      k_red_read<<<1, 1, 0, pd.stream>>>(pd.st.p, pd.rc, pd.scratch4.p);
+      I.note_launch("k_red_read");
+    }
+    CK(cudaGetLastError());
+    sync_all();
+    double out[RED_W];
+    I.set_dev(I.P(0));
+    CK(cudaMemcpy(out, I.P(0).scratch4.p, sizeof(out), cudaMemcpyDeviceToHost));
+    check_device_error();
+    return out[3];
+  };
+  for (size_t i = 0; i < np; ++i) {
+    PartDev& pd = I.P(i);
+    I.set_dev(pd);
+    CK(cudaEventRecord(pd.ev0, pd.stream));
+    CK(cudaMemsetAsync(pd.xsol.p, 0, sizeof(double) * (size_t)pd.lev[0]->n_own, pd.stream));
+  }
+  // r lives in V_0 until it is normalised
+  auto R = [&](size_t i) -> const double* { return V(i, 0); };
+  for (size_t i = 0; i < np; ++i) {
+    PartDev& pd = I.P(i);
+    I.set_dev(pd);
+    CK(cudaMemcpyAsync(V(i, 0), pd.bsave.p, sizeof(double) * (size_t)pd.lev[0]->n_own, cudaMemcpyDeviceToDevice, pd.stream));
+  }
+  const double beta0 = std::sqrt(host_dot(R, R));
+  if (hist) hist[0] = beta0;
+  int it = 0;
+  bool done = (beta0 == 0.0 || maxiter == 0);
+  std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
+  double est = beta0;
+  bool first = true;
+  while (!done) {
+    const double beta = first ? beta0 : std::sqrt(host_dot(R, R));
+    first = false;
+    for (size_t i = 0; i < np; ++i) {
+      PartDev& pd = I.P(i);
+      I.set_dev(pd);
+      const int n = (int)pd.lev[0]->n_own;
+      k_div<<<I.grid_for(n, BLOCK * 4), BLOCK, 0, pd.stream>>>(V(i, 0), V(i, 0), beta, n, pd.st.p);
+      I.note_launch("k_div");
+    }
+    std::fill(H.begin(), H.end(), 0.0);
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int j = 0;
+    while (j < m) {
+      if (pre) {  // z_j = M^-1 v_j
+        for (size_t i = 0; i < np; ++i) {
+          PartDev& pd = I.P(i);
+          I.set_dev(pd);
+          CK(cudaMemcpyAsync(pd.lev[0]->b.p, V(i, j), sizeof(double) * (size_t)pd.lev[0]->n_own, cudaMemcpyDeviceToDevice, pd.stream));
+        }
+        if (use_graph)
+          launch_graphs(I.g_vcycle, I.g_vcycle_nodes);
+        else
+          enqueue_vcycle_entry();
+        for (size_t i = 0; i < np; ++i) {
+          PartDev& pd = I.P(i);
+          I.set_dev(pd);
+          CK(cudaMemcpyAsync(Z(i, j), pd.lev[0]->x.p, sizeof(double) * (size_t)pd.lev[0]->n_own, cudaMemcpyDeviceToDevice, pd.stream));
+        }
+      }
+      {  // w = A z_j, into V_{j+1}
+        std::vector<EpiArgs> epi(np);
+        std::vector<const double*> xin(np);
+        for (size_t i = 0; i < np; ++i) {
+          xin[i] = Z(i, j);
+          epi[i] = EpiArgs{V(i, j + 1), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+        }
+        OpSpec op{0, PAMG_A_OO, 0, M_MUL, false, 0, false};
+        enqueue_op(op, xin, epi);
+      }
+      for (int k = 0; k <= j + 1; ++k) {  // k <= j: h_kj = <w, v_k>, w -= h_kj v_k ; k = j + 1: h_{j+1,j} = ||w||, v_{j+1} = w / h
+        for (size_t i = 0; i < np; ++i) {
+          PartDev& pd = I.P(i);
+          I.set_dev(pd);
+          const int n = (int)pd.lev[0]->n_own;
+          k_dot<<<I.grid_red(n), BLOCK, 0, pd.stream>>>(V(i, j + 1), k <= j ? V(i, k) : V(i, j + 1), n, pd.st.p, pd.partials.p, pd.rc, 3, 0);
+          I.note_launch("k_dot");
+        }
+        for (size_t i = 0; i < np; ++i) {
+          PartDev& pd = I.P(i);
+          I.set_dev(pd);
+          const int n = (int)pd.lev[0]->n_own;
+          if (k <= j)
+            k_gs_sub<<<I.grid_for(n, BLOCK * 4), BLOCK, 0, pd.stream>>>(V(i, j + 1), V(i, k), n, pd.st.p, pd.rc, pd.gm_h.p + k);
+          else
+            k_gs_norm<<<I.grid_for(n, BLOCK * 4), BLOCK, 0, pd.stream>>>(V(i, j + 1), n, pd.st.p, pd.rc, pd.gm_h.p + k);
+          I.note_launch(k <= j ? "k_gs_sub" : "k_gs_norm");
+        }
+      }
+      CK(cudaGetLastError());
+      sync_all();
+      I.set_dev(I.P(0));
+      CK(cudaMemcpy(hcol.data(), I.P(0).gm_h.p, sizeof(double) * (size_t)(j + 2), cudaMemcpyDeviceToHost));
+      check_device_error();
+      for (int k = 0; k <= j + 1; ++k) H[(size_t)k * m + j] = hcol[k];
+      for (int k = 0; k < j; ++k) {  // previous rotations on the new column
+        const double t = cs[k] * H[(size_t)k * m + j] + sn[k] * H[(size_t)(k + 1) * m + j];
+        H[(size_t)(k + 1) * m + j] = -sn[k] * H[(size_t)k * m + j] + cs[k] * H[(size_t)(k + 1) * m + j];
+        H[(size_t)k * m + j] = t;
+      }
+      const double d = std::hypot(H[(size_t)j * m + j], H[(size_t)(j + 1) * m + j]);
+      cs[j] = H[(size_t)j * m + j] / d;
+      sn[j] = H[(size_t)(j + 1) * m + j] / d;
+      H[(size_t)j * m + j] = d;
+      H[(size_t)(j + 1) * m + j] = 0.0;
+      g[j + 1] = -sn[j] * g[j];
+      g[j] = cs[j] * g[j];
+      ++j;
+      ++it;
+      est = std::fabs(g[j]);
+      if (hist) hist[it] = est;
+      if (est <= rtol * beta0 || it >= maxiter) {
+        done = true;
+        break;
+      }
+    }
+    for (int i2 = j - 1; i2 >= 0; --i2) {  // back substitution
+      double s2 = 0.0;
+      for (int k = i2 + 1; k < j; ++k) s2 += H[(size_t)i2 * m + k] * y[k];
+      y[i2] = (g[i2] - s2) / H[(size_t)i2 * m + i2];
+    }
+    for (int k = 0; k < j; ++k)  // x += y_k z_k, ascending k
+      for (size_t i = 0; i < np; ++i) {
+        PartDev& pd = I.P(i);
+        I.set_dev(pd);
+        const int n = (int)pd.lev[0]->n_own;
+        k_axpy<<<I.grid_for(n, BLOCK * 4), BLOCK, 0, pd.stream>>>(pd.xsol.p, Z(i, k), y[k], n, pd.st.p);
+        I.note_launch("k_axpy");
+      }
+    if (!done) {  // r = b - A x, into V_0
+      std::vector<EpiArgs> epi(np);
+      std::vector<const double*> xin(np);
+      for (size_t i = 0; i < np; ++i) {
+        xin[i] = I.P(i).xsol.p;
+        epi[i] = EpiArgs{V(i, 0), I.P(i).bsave.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, 0.0};
+      }
+      OpSpec op{0, PAMG_A_OO, 0, M_RESID, false, 0, false};
+      enqueue_op(op, xin, epi);
+    }
+  }
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventRecord(up->ev1, up->stream));
+  }
+  CK(cudaGetLastError());
+  sync_all();
+  float ms = 0, mx = 0;
+  for (auto& up : I.parts) {
+    I.set_dev(*up);
+    CK(cudaEventElapsedTime(&ms, up->ev0, up->ev1));
+    mx = std::max(mx, ms);
+  }
+  check_device_error();
+  read_solution(x);
+  const bool conv = est <= rtol * beta0;
+  if (iters) *iters = it;
+  I.stats.iters = it;
+  I.stats.converged = conv;
+  I.stats.r0_norm = beta0;
+  I.stats.r_norm = est;
   I.stats.solve_ms = mx;
   I.stats.kernel_launches = I.launches;
   return conv ? PAMG_OK : PAMG_ERR_NOTCONV;

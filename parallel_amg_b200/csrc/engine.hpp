@@ -48,6 +48,8 @@ class Engine {
   double dot(int level, const double* const* u, const double* const* v);
   void vcycle(const double* const* b, double* const* x);
   int pcg(const double* const* b, double* const* x, double rtol, int maxiter, int mode, int* iters, double* hist);
+  int fgmres(const double* const* b, double* const* x, double rtol, int maxiter, int restart, int precond, int* iters,
+             double* hist);
   void load_rhs(const double* const* b);
   int pcg_resident(double rtol, int maxiter, int mode, int* iters, double* hist);
   void read_solution(double* const* x);

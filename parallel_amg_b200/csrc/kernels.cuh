@@ -1643,6 +1643,52 @@ __global__ void __launch_bounds__(BLOCK) k_dot2(const double* __restrict__ r, co
     }
   }
 }
+// ---------------------------------------------------------------------------------------------
+// FGMRES vector kernels (oracle/amg_oracle.py fgmres).  The Arnoldi coefficients stay on the device between
+// the dot that produces them and the update that consumes them (the same publish / consume pair as PCG's scalars); the host
+// reads one Hessenberg column per inner step for the Givens rotations and the convergence decision.
+// ---------------------------------------------------------------------------------------------
+// dst = src / d
+__global__ void __launch_bounds__(BLOCK) k_div(const double* src, double* dst, double d, int n, DevState* st) {
+  trace_mark(st);
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) dst[i] = __ddiv_rn(src[i], d);
+}
+// modified Gram-Schmidt step: h = <w, v> (slot 3 of the all-reduce published by the k_dot before) ; w -= h v ; hcol[0] = h
+__global__ void __launch_bounds__(BLOCK) k_gs_sub(double* __restrict__ w, const double* __restrict__ v, int n, DevState* st, RedCtx rc,
+                                                   double* hcol) {
+  trace_mark(st);
+  __shared__ double s_h;
+  if (threadIdx.x == 0) {
+    double r[RED_W];
+    red_consume(st, rc, r);
+    s_h = r[3];
+    if (blockIdx.x == 0) hcol[0] = r[3];
+  }
+  __syncthreads();
+  const double h = s_h;
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) w[i] = __dsub_rn(w[i], __dmul_rn(h, v[i]));
+}
+// h_{j+1,j} = sqrt(<w, w>) ; v_{j+1} = w / h_{j+1,j} (in place; left as it is when the norm is 0: a lucky breakdown)
+__global__ void __launch_bounds__(BLOCK) k_gs_norm(double* __restrict__ w, int n, DevState* st, RedCtx rc, double* hcol) {
+  trace_mark(st);
+  __shared__ double s_h;
+  if (threadIdx.x == 0) {
+    double r[RED_W];
+    red_consume(st, rc, r);
+    s_h = sqrt(r[3]);
+    if (blockIdx.x == 0) hcol[0] = s_h;
+  }
+  __syncthreads();
+  const double h = s_h;
+  if (h == 0.0) return;
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) w[i] = __ddiv_rn(w[i], h);
+}
+// x += a z
+__global__ void __launch_bounds__(BLOCK) k_axpy(double* __restrict__ x, const double* __restrict__ z, double a, int n, DevState* st) {
+  trace_mark(st);
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) x[i] = __dadd_rn(x[i], __dmul_rn(a, z[i]));
+}
+
 __global__ void k_red_read(DevState* st, RedCtx rc, double* out4) {
   double v[RED_W];
   red_consume(st, rc, v);

@@ -37,3 +37,29 @@ def test_c_oracle_matches_python_oracle(dims, pp, oopts):
     x, it, hist = co.pcg(own_parts(lev, b), precond=False, maxiter=400)
     xs, it_ref, _ = O.pcg(h, O.pvector_from_global(lev, b), precond=False, maxiter=400)
     assert it == it_ref
+
+
+@pytest.mark.parametrize("dims,pp,oopts", [
+    ((40, 40), (2, 2), {}),
+    ((14, 14, 14), (2, 2, 1), {}),
+    ((30, 30), (2, 1), {"cycle": "w", "coarse_size": 40}),
+])
+def test_c_oracle_fgmres_matches_python_oracle(dims, pp, oopts):
+    """orc_fgmres against amg_oracle.fgmres: identical inner iteration counts, residual estimates, solutions; with a restart short
+    enough to be taken, without preconditioner (plain restarted GMRES), and truncated by maxiter."""
+    A, owner, h = oracle_problem(dims, pp, tuple(sorted(oopts.items())))
+    co = c_oracle.COracle.from_oracle_hierarchy(h)
+    lev = h["levels"][0]
+    n = A.shape[0]
+    b = A @ det_vector(n, 5)
+    for kw in ({}, {"restart": 4}, {"precond": False, "restart": 10, "maxiter": 300}, {"maxiter": 3}, {"maxiter": 0}):
+        xs, it_ref, hist_ref = O.fgmres(h, O.pvector_from_global(lev, b), **kw)
+        x, it, hist = co.fgmres(own_parts(lev, b), **kw)
+        assert it == it_ref, kw
+        assert np.allclose(hist, hist_ref, rtol=1e-7), kw
+        assert rel_err(x, own_of(lev, xs)) <= 1e-9, kw
+    xs, it, hist = O.fgmres(h, O.pvector_from_global(lev, b))
+    x = np.zeros(n)
+    for d, v in zip(lev["parts"], xs):
+        x[d["own_to_global"]] = v[: len(d["own_to_global"])]
+    assert np.linalg.norm(b - A @ x) <= 1.0001e-8 * np.linalg.norm(b)          # the estimate is the true residual norm

@@ -404,3 +404,49 @@ def test_flexible_cg_parity(dims, pp, oopts):
     x2, it2, hist2, ok2 = c.pcg(own_parts(lev, rhs))     # switching drivers on one context re-captures the iteration graph
     xs2, it_ref2, hist_ref2 = O.pcg(h, O.pvector_from_global(lev, rhs))
     assert ok2 and it2 == it_ref2 and np.allclose(hist2, hist_ref2, rtol=1e-7)
+
+
+@pytest.mark.parametrize("dims,pp", PROBLEMS)
+@pytest.mark.parametrize("oopts", [{}, {"cycle": "w", "coarse_size": 40}], ids=["v", "w"])
+def test_fgmres_parity(dims, pp, oopts):
+    """pamg_fgmres: restarted flexible GMRES right-preconditioned by one cycle against the oracle's fgmres -- identical inner
+    iteration counts, residual estimates to 1e-7, solutions; with a restart that is taken, without preconditioner, truncated."""
+    A, h, c = make(dims, pp, oopts)
+    lev = h["levels"][0]
+    n = A.shape[0]
+    rhs = A @ det_vector(n, 83)
+    for kw in ({}, {"restart": 4}, {"precond": False, "restart": 12, "maxiter": 60}, {"maxiter": 3}, {"maxiter": 0}):
+        xs, it_ref, hist_ref = O.fgmres(h, O.pvector_from_global(lev, rhs), **kw)
+        x, it, hist, ok = c.fgmres(own_parts(lev, rhs), **kw)
+        assert it == it_ref, kw
+        assert ok == (hist_ref[-1] <= 1e-8 * hist_ref[0]), kw
+        assert np.allclose(hist, hist_ref, rtol=1e-7), kw
+        assert rel_err(x, own_of(lev, xs)) <= 1e-9, kw
+    x2, it2, hist2, ok2 = c.pcg(own_parts(lev, rhs))     # the Krylov drivers share one context
+    xs2, it_ref2, hist_ref2 = O.pcg(h, O.pvector_from_global(lev, rhs))
+    assert ok2 and it2 == it_ref2 and np.allclose(hist2, hist_ref2, rtol=1e-7)
+
+
+def test_fgmres_nonsymmetric_operator():
+    """What GMRES is for: a non-symmetric operator (convection added to the 2-D Poisson values, same pattern), hierarchy built
+    by the oracle from the symmetric part's pattern; CG is not applicable, FGMRES must match the oracle step for step."""
+    import scipy.sparse as sp
+    dims, pp = (40, 40), (2, 2)
+    A0 = O.poisson_fd(dims).tocsr()
+    A = A0.copy()
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    A.data = A.data + 0.3 * np.sign(A.indices - rows) * (np.abs(A.indices - rows) == 1)   # upwind-ish skew part along x
+    owner = O.uniform_partition(pp, dims)
+    h = O.build(sp.csr_matrix(A), owner, int(np.prod(pp)), {})
+    c = product_context_from_oracle(h, None)
+    c.device_init()
+    lev = h["levels"][0]
+    rhs = A @ det_vector(A.shape[0], 9)
+    xs, it_ref, hist_ref = O.fgmres(h, O.pvector_from_global(lev, rhs), restart=20)
+    x, it, hist, ok = c.fgmres(own_parts(lev, rhs), restart=20)
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
+    assert rel_err(x, own_of(lev, xs)) <= 1e-9
+    xg = np.zeros(A.shape[0])
+    for d, v in zip(lev["parts"], x):
+        xg[d["own_to_global"]] = v
+    assert np.linalg.norm(rhs - A @ xg) <= 1.001e-8 * np.linalg.norm(rhs)

@@ -90,3 +90,27 @@ def test_l1_jacobi_and_two_sweeps_at_size():
         assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
         co.close()
         c.close()
+
+
+@pytest.mark.parametrize("kind,dims,pp,opts", [("poisson", (96, 96, 96), (2, 1, 1), {}), ("jump", (64, 64, 64), (1, 1, 1), dict(eps_strength=0.08))],
+                         ids=["poisson-96-p2", "jump-64-p1"])
+def test_fgmres_at_size_matches_c_oracle(kind, dims, pp, opts):
+    """pamg_fgmres through the production kernels (SELL, persistent CTAs) against orc_fgmres on the same operators: identical
+    inner iteration counts with and without a restart inside the solve, estimates to 1e-7, and the true residual."""
+    c, nparts = _context(kind, dims, pp, opts)
+    co = c_oracle.COracle.from_product_context(c, nparts)
+    n, _ = c.global_size()
+    own = [c.index_maps(0, p)[0] for p in range(nparts)]
+    rhs = c.host_matvec_global(det_vector(n, 1))
+    for restart in (30, 6):
+        x_ref, it_ref, hist_ref = co.fgmres([rhs[o] for o in own], 1e-8, 400, restart, True)
+        x, it, hist, ok = c.fgmres([rhs[o] for o in own], rtol=1e-8, maxiter=400, restart=restart)
+        assert ok and it == it_ref, (it, it_ref)
+        assert np.allclose(hist, hist_ref, rtol=1e-7)
+        assert rel_err(x, x_ref) <= 1e-9
+        xg = np.zeros(n)
+        for o, xp in zip(own, x):
+            xg[o] = xp
+        assert np.linalg.norm(c.host_matvec_global(xg) - rhs) <= 1.01e-8 * np.linalg.norm(rhs)
+    co.close()
+    c.close()
