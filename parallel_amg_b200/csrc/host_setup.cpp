@@ -535,6 +535,49 @@ static int64_t aggregate_part(const Csr& A, const std::vector<int32_t>& owner, c
   return nagg;
 }
 
+// every part: on the device when the matrix (or node graph) is resident there (setup_gpu.cu gpu_aggregate:
+// same aggregates bit for bit), else one part per thread on the host.  agg_gid[g] = aggregate id inside the owner part.
+static void aggregate_all(const Csr& M, const GpuMat* dM, const std::vector<int32_t>& owner, const OwnIndex& oi, int32_t nparts,
+                          double eps, const std::vector<double>& absdiag, std::vector<int32_t>& agg_gid,
+                          std::vector<int64_t>& counts, bool* on_gpu) {
+  const int64_t n = M.nrows;
+  agg_gid.resize(n);
+  counts.assign(nparts, 0);
+  *on_gpu = false;
+  const char* e = std::getenv("PAMG_GPU_AGG");  // 0: host walk; 2: the device or an error (tests); default: device, host as fallback
+  const int mode = e ? std::atoi(e) : 1;
+  std::string why = "the matrix is not resident on a device";
+  if (dM && mode != 0) {
+    try {
+      std::vector<int64_t> part_off(nparts + 1, 0);
+      for (int32_t p = 0; p < nparts; ++p) part_off[p + 1] = part_off[p] + (int64_t)oi.own[p].size();
+      std::vector<int32_t> pos(n);
+#pragma omp parallel for schedule(static)
+      for (int64_t g = 0; g < n; ++g) pos[g] = (int32_t)(part_off[owner[g]] + oi.lid[g]);
+      if (gpu_aggregate(dM, owner.data(), pos.data(), part_off.data(), nparts, eps, agg_gid.data(), counts.data())) {
+        *on_gpu = true;
+        return;
+      }
+      why = "the strength graph is not symmetric or its dependency chain is too long";
+    } catch (const std::exception& ex) {
+      why = ex.what();
+      std::fprintf(stderr, "[pamg setup] GPU aggregation failed (%s): falling back to the host\n", ex.what());
+    }
+  }
+  if (mode == 2) throw std::runtime_error("PAMG_GPU_AGG=2 but the aggregation could not run on the device: " + why);
+  std::vector<std::vector<int32_t>> aggs(nparts);
+  OmpGuard og;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int32_t p = 0; p < nparts; ++p) og.run([&] { counts[p] = aggregate_part(M, owner, oi, p, eps, absdiag, aggs[p]); });
+  og.rethrow();
+  for (int32_t p = 0; p < nparts; ++p) {
+    const auto& own = oi.own[p];
+    const auto& a = aggs[p];
+#pragma omp parallel for schedule(static)
+    for (int64_t li = 0; li < (int64_t)own.size(); ++li) agg_gid[own[li]] = a[li];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // smoothed prolongator P = (I - w D_F^-1 A_F) P0, w = 4/(3 rho_F)       (App. B items 3-4)
 // ------------------------------------------------------------------------------------------
@@ -1100,7 +1143,7 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     tm.lap("own index + diagonal", (int)g.size() - 1);
     if (n <= o.coarse_size || (int32_t)g.size() >= o.max_levels) break;
 
-    std::vector<std::vector<int32_t>> aggs(nparts);
+    std::vector<int32_t> agg_gid;  // aggregate id inside the owner part, by row (scalar) or node (near-nullspace) gid
     std::vector<int64_t> counts(nparts, 0);
     std::vector<int64_t> off(nparts + 1, 0);
     Csr P0;
@@ -1108,13 +1151,10 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     std::vector<double> Bc;
     int64_t nc = 0;
     int kdof = 1;
+    bool agg_on_gpu = false;
     cur.agg_loc.resize(n);
     if (!use_ns) {
-      OmpGuard og;
-#pragma omp parallel for schedule(dynamic, 1)
-      for (int32_t p = 0; p < nparts; ++p)
-        og.run([&] { counts[p] = aggregate_part(cur.A(), cur.owner, cur.oi, p, eps, absdiag, aggs[p]); });
-      og.rethrow();
+      aggregate_all(cur.A(), dA, cur.owner, cur.oi, nparts, eps, absdiag, agg_gid, counts, &agg_on_gpu);
       for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
       nc = off[nparts];
       if (nc >= n) break;
@@ -1123,12 +1163,12 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       P0.ptr.resize(n + 1);
       P0.col.resize(n);
       P0.val.assign(n, 1.0);
-      for (int64_t i = 0; i <= n; ++i) P0.ptr[i] = i;
-      for (int32_t p = 0; p < nparts; ++p) {
-        const auto& own = cur.oi.own[p];
-        for (size_t li = 0; li < own.size(); ++li) {
-          cur.agg_loc[own[li]] = aggs[p][li];
-          P0.col[own[li]] = off[p] + aggs[p][li];
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i <= n; ++i) {
+        P0.ptr[i] = i;
+        if (i < n) {
+          cur.agg_loc[i] = agg_gid[i];
+          P0.col[i] = off[cur.owner[i]] + agg_gid[i];
         }
       }
     } else {
@@ -1147,25 +1187,34 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       OwnIndex oin;
       build_own_index(owner_node, nparts, oin);
       std::vector<double> none;
-      OmpGuard og;
-#pragma omp parallel for schedule(dynamic, 1)
-      for (int32_t p = 0; p < nparts; ++p) og.run([&] { counts[p] = aggregate_part(N, owner_node, oin, p, 0.0, none, aggs[p]); });
-      og.rethrow();
+      GpuMat* dN = nullptr;
+      if (gpu && dA) {
+        try {
+          dN = gpu_upload(N);
+        } catch (const std::exception&) {
+          dN = nullptr;
+        }
+      }
+      try {
+        aggregate_all(N, dN, owner_node, oin, nparts, 0.0, none, agg_gid, counts, &agg_on_gpu);
+      } catch (...) {
+        gpu_free(dN);
+        throw;
+      }
+      gpu_free(dN);
       for (int32_t p = 0; p < nparts; ++p) off[p + 1] = off[p] + counts[p];
       const int64_t nagg = off[nparts];
       nc = nagg * kdof;
       if (nc >= n) break;
       std::vector<int64_t> agg_node(nn);
-      for (int32_t p = 0; p < nparts; ++p) {
-        const auto& own = oin.own[p];
-        for (size_t li = 0; li < own.size(); ++li) {
-          agg_node[own[li]] = off[p] + aggs[p][li];
-          for (int d = 0; d < bs; ++d) cur.agg_loc[own[li] * bs + d] = aggs[p][li];
-        }
+#pragma omp parallel for schedule(static)
+      for (int64_t v = 0; v < nn; ++v) {
+        agg_node[v] = off[owner_node[v]] + agg_gid[v];
+        for (int d = 0; d < bs; ++d) cur.agg_loc[v * bs + d] = agg_gid[v];
       }
       tentative_from_nullspace(Bcur, kdof, bs, agg_node, nagg, P0, Bc, dead);
     }
-    tm.lap("aggregation + P0", (int)g.size() - 1);
+    tm.lap(agg_on_gpu ? "aggregation (GPU) + P0" : "aggregation + P0", (int)g.size() - 1);
     GpuMat *dP = nullptr, *dR = nullptr;  // resident copies of P and R (GPU chain)
     build_prolongator(cur.A(), P0, nc, eps, absdiag, cur.P, &cur.omega_p, gpu, dA, &dP);
     tm.lap(dP ? "prolongator smoothing (GPU)" : "prolongator smoothing", (int)g.size() - 1);

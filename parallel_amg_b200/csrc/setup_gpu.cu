@@ -519,6 +519,277 @@ GpuMat* gpu_transpose(const GpuMat* A) {
   return T.release();
 }
 
+// ------------------------------------------------------------------------------------------------
+// the greedy three-pass aggregation on the GPU, bit-identical to host_setup.cpp aggregate_part
+// ------------------------------------------------------------------------------------------------
+// The host algorithm walks the rows of a part in ascending order; what it decides for row i depends only on rows before
+// i.  Restated without the walk (S = strong own-own neighbours, symmetric; all parts at once: no strong edge joins two
+// parts, and inside a part ascending global id IS ascending local id):
+//   pass 1  i is a ROOT  <=>  no ROOT r < i within distance 2 of i in S   (r's closed neighbourhood already holds one
+//           of i's).  That is the lexicographically first maximal independent set of S^2.  Fixed point: an undecided i
+//           becomes NOT as soon as one earlier vertex within distance 2 is a ROOT, ROOT as soon as all of them are NOT.
+//           Every decision rests on final facts only, so any evaluation order (rounds, stale reads) gives the same set.
+//           A blocked vertex remembers its LARGEST undecided earlier neighbour and is not rescanned until that one is
+//           decided (the front moves in id order, so the largest one is the last to go).
+//           aggregate id = rank of the root among the roots of its part (exclusive scan in part-major order);
+//           a non-root takes the id of the root it is adjacent to (closed neighbourhoods of roots are disjoint).
+//   pass 2  a vertex pass 1 left out joins the first neighbour (ascending column) that pass 1 aggregated.
+//   pass 3  is empty when S is symmetric: the root set is MAXIMAL in S^2, so every vertex has a root within distance 2 --
+//           at distance 1 pass 1 aggregated it, at distance 2 one of its neighbours is adjacent to that root and pass 2
+//           picks it up (isolated vertices are roots).  The device checks that nothing is left and that S is symmetric;
+//           otherwise (a non-symmetric operator, values within rounding of the threshold) the host walks the rows.
+// The strength test repeats the host's arithmetic (|a_ij| > eps sqrt(|a_ii| |a_jj|), every operation rounded once).
+namespace {
+
+enum : unsigned char { ST_U = 0, ST_ROOT = 1, ST_NOT = 2 };
+
+__device__ __forceinline__ unsigned char ld_state(const unsigned char* p) { return __ldcg(p); }
+
+__global__ void k_absdiag(const int64_t* __restrict__ ptr, const int32_t* __restrict__ col, const double* __restrict__ val, int64_t n,
+                          double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  double d = 0.0;
+  for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k)
+    if (col[k] == i) d = val[k];
+  out[i] = fabs(d);
+}
+
+__device__ __forceinline__ bool is_strong(int64_t i, int32_t j, double v, const int32_t* __restrict__ owner, double eps,
+                                          const double* __restrict__ ad) {
+  if ((int64_t)j == i || owner[j] != owner[i]) return false;
+  if (eps <= 0.0) return true;
+  return fabs(v) > __dmul_rn(eps, __dsqrt_rn(__dmul_rn(ad[i], ad[j])));
+}
+
+// FILL = false: cnt[i] = strong neighbours of row i ; FILL = true: their columns (ascending, A's order) at s_ptr[i]
+template <bool FILL>
+__global__ void k_strong(const int64_t* __restrict__ ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                         const int32_t* __restrict__ owner, double eps, const double* __restrict__ ad, int64_t n,
+                         int64_t* __restrict__ cnt, const int64_t* __restrict__ s_ptr, int32_t* __restrict__ s_col) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  int64_t q = FILL ? s_ptr[i] : 0;
+  for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k)
+    if (is_strong(i, col[k], val[k], owner, eps, ad)) {
+      if (FILL) s_col[q] = col[k];
+      ++q;
+    }
+  if (!FILL) cnt[i] = q;
+}
+
+// every strong edge i -> j must have its twin j -> i (binary search in row j)
+__global__ void k_sym_check(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, int64_t n, unsigned long long* bad) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t q = sp[i]; q < sp[i + 1]; ++q) {
+    const int32_t j = sc[q];
+    int64_t lo = sp[j], hi = sp[j + 1];
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)sc[mid] < i)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo >= sp[j + 1] || (int64_t)sc[lo] != i) atomicAdd(bad, 1ull);
+  }
+}
+
+// one round of the fixed point (distance 2); *left = vertices still undecided after it
+__global__ void k_mis_round(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, int64_t n, unsigned char* state,
+                            int32_t* __restrict__ blocker, unsigned long long* left) {
+  unsigned long long mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TB) {
+    if (ld_state(state + i) != ST_U) continue;
+    const int32_t b = blocker[i];
+    if (b >= 0 && ld_state(state + b) == ST_U) {
+      ++mine;
+      continue;
+    }
+    bool has_root = false;
+    int32_t maxu = -1;
+    const int64_t e0 = sp[i + 1];
+    for (int64_t q = sp[i]; q < e0 && !has_root; ++q) {
+      const int32_t v = sc[q];
+      if ((int64_t)v < i) {
+        const unsigned char s = ld_state(state + v);
+        if (s == ST_ROOT)
+          has_root = true;
+        else if (s == ST_U)
+          maxu = max(maxu, v);
+      }
+      {
+        const int64_t e1 = sp[v + 1];
+        for (int64_t q2 = sp[v]; q2 < e1 && !has_root; ++q2) {
+          const int32_t k = sc[q2];
+          if ((int64_t)k < i) {
+            const unsigned char s = ld_state(state + k);
+            if (s == ST_ROOT)
+              has_root = true;
+            else if (s == ST_U)
+              maxu = max(maxu, k);
+          }
+        }
+      }
+    }
+    if (has_root) {
+      state[i] = ST_NOT;
+    } else if (maxu < 0) {
+      state[i] = ST_ROOT;
+    } else {
+      blocker[i] = maxu;
+      ++mine;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(left, mine);
+}
+
+// flags[pos[g]] = 1 for the roots (part-major order: its exclusive scan ranks the roots inside every part); flags[n] = 0
+__global__ void k_root_flags(const unsigned char* __restrict__ state, const int32_t* __restrict__ pos, int64_t n, int64_t* __restrict__ flags) {
+  const int64_t g = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (g < n) flags[pos[g]] = state[g] == ST_ROOT ? 1 : 0;
+  if (g == n) flags[n] = 0;
+}
+__global__ void k_gather_i64(const int64_t* __restrict__ src, const int64_t* __restrict__ idx, int n, int64_t* __restrict__ out) {
+  const int i = blockIdx.x * TB + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+// pass 1 ids: the root's rank inside its part, for the root and its neighbours; -1 elsewhere
+__global__ void k_agg_pass1(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, int64_t n, const unsigned char* __restrict__ state,
+                            const int32_t* __restrict__ pos, const int32_t* __restrict__ owner, const int64_t* __restrict__ rank,
+                            const int64_t* __restrict__ base, int32_t* __restrict__ agg) {
+  const int64_t v = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (v >= n) return;
+  int64_t r = -1;
+  if (state[v] == ST_ROOT) {
+    r = v;
+  } else {
+    for (int64_t q = sp[v]; q < sp[v + 1]; ++q)
+      if (state[sc[q]] == ST_ROOT) {
+        r = sc[q];
+        break;
+      }
+  }
+  agg[v] = r < 0 ? -1 : (int32_t)(rank[pos[r]] - base[owner[r]]);
+}
+// pass 2 (reads pass-1 ids only); *left counts what would remain for pass 3 (none when S is symmetric)
+__global__ void k_agg_pass2(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, int64_t n, const int32_t* __restrict__ agg1,
+                            int32_t* __restrict__ agg2, unsigned long long* left) {
+  const int64_t v = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (v >= n) return;
+  int32_t a = agg1[v];
+  if (a == -1)
+    for (int64_t q = sp[v]; q < sp[v + 1]; ++q)
+      if (agg1[sc[q]] != -1) {
+        a = agg1[sc[q]];
+        break;
+      }
+  agg2[v] = a;
+  if (a == -1) atomicAdd(left, 1ull);
+}
+// runs the fixed point to the end; false: gave up (a dependency chain longer than max_rounds, e.g. a 1-D problem)
+bool mis_rounds(const int64_t* sp, const int32_t* sc, int64_t n, unsigned char* state, int32_t* blocker, int64_t max_rounds, int64_t* rounds_out) {
+  constexpr int BATCH = 48;
+  Buf<unsigned long long> d_left;
+  d_left.alloc(BATCH);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + TB - 1) / TB, 148 * 16));
+  int64_t rounds = 0;
+  while (true) {
+    GK(cudaMemset(d_left.p, 0, BATCH * sizeof(unsigned long long)));
+    for (int r = 0; r < BATCH; ++r) k_mis_round<<<grid, TB>>>(sp, sc, n, state, blocker, d_left.p + r);
+    GK(cudaGetLastError());
+    rounds += BATCH;
+    unsigned long long left = 0;
+    GK(cudaMemcpy(&left, d_left.p + (BATCH - 1), sizeof(left), cudaMemcpyDeviceToHost));
+    if (left == 0) break;
+    if (rounds > max_rounds) return false;
+  }
+  if (rounds_out) *rounds_out = rounds;
+  return true;
+}
+
+}  // namespace
+
+bool gpu_aggregate(const GpuMat* A, const int32_t* owner, const int32_t* pos, const int64_t* part_off, int32_t nparts, double eps,
+                   int32_t* agg_by_gid, int64_t* counts) {
+  const int64_t n = A->nrows;
+  if (n == 0) {
+    for (int32_t p = 0; p < nparts; ++p) counts[p] = 0;
+    return true;
+  }
+  if (n >= ((int64_t)1 << 31) - 1) return false;
+  const int g_n = (int)((n + TB - 1) / TB), g_n1 = (int)((n + 1 + TB - 1) / TB);
+  Buf<int32_t> d_owner, d_pos;
+  d_owner.upload(owner, (size_t)n);
+  d_pos.upload(pos, (size_t)n);
+  Buf<double> d_ad;
+  if (eps > 0.0) {
+    d_ad.alloc(n);
+    k_absdiag<<<g_n, TB>>>(A->ptr.p, A->col.p, A->val.p, n, d_ad.p);
+  }
+  // strength graph S
+  Buf<int64_t> d_cnt, s_ptr;
+  Buf<int32_t> s_col;
+  Buf<char> tmp;
+  d_cnt.alloc(n + 1);
+  GK(cudaMemset(d_cnt.p, 0, (n + 1) * sizeof(int64_t)));
+  k_strong<false><<<g_n, TB>>>(A->ptr.p, A->col.p, A->val.p, d_owner.p, eps, d_ad.p, n, d_cnt.p, nullptr, nullptr);
+  s_ptr.alloc(n + 1);
+  exclusive_scan_i64(d_cnt.p, s_ptr.p, n + 1, tmp);
+  int64_t s_nnz = 0;
+  GK(cudaMemcpy(&s_nnz, s_ptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  s_col.alloc(std::max<int64_t>(s_nnz, 1));
+  k_strong<true><<<g_n, TB>>>(A->ptr.p, A->col.p, A->val.p, d_owner.p, eps, d_ad.p, n, nullptr, s_ptr.p, s_col.p);
+  Buf<unsigned long long> d_flag;
+  d_flag.alloc(2);
+  GK(cudaMemset(d_flag.p, 0, 2 * sizeof(unsigned long long)));
+  k_sym_check<<<g_n, TB>>>(s_ptr.p, s_col.p, n, d_flag.p);
+  unsigned long long bad = 0;
+  GK(cudaMemcpy(&bad, d_flag.p, sizeof(bad), cudaMemcpyDeviceToHost));
+  if (bad) return false;  // not symmetric (values near the threshold, or a non-symmetric operator): the host walks the rows
+  // pass 1
+  Buf<unsigned char> state;
+  Buf<int32_t> blocker, agg1, agg2;
+  state.alloc(n);
+  blocker.alloc(n);
+  agg1.alloc(n);
+  agg2.alloc(n);
+  GK(cudaMemset(state.p, ST_U, n));
+  GK(cudaMemset(blocker.p, 0xff, n * sizeof(int32_t)));
+  const char* mr = getenv("PAMG_GPU_AGG_MAX_ROUNDS");
+  const int64_t max_rounds = mr ? atoll(mr) : 40000;
+  int64_t rounds1 = 0;
+  if (!mis_rounds(s_ptr.p, s_col.p, n, state.p, blocker.p, max_rounds, &rounds1)) return false;
+  Buf<int64_t> flags, rank, d_off, base1;
+  flags.alloc(n + 1);
+  rank.alloc(n + 1);
+  d_off.upload(part_off, (size_t)nparts + 1);
+  base1.alloc(nparts + 1);
+  k_root_flags<<<g_n1, TB>>>(state.p, d_pos.p, n, flags.p);
+  exclusive_scan_i64(flags.p, rank.p, n + 1, tmp);
+  k_gather_i64<<<(nparts + 1 + TB - 1) / TB, TB>>>(rank.p, d_off.p, nparts + 1, base1.p);
+  k_agg_pass1<<<g_n, TB>>>(s_ptr.p, s_col.p, n, state.p, d_pos.p, d_owner.p, rank.p, base1.p, agg1.p);
+  std::vector<int64_t> b1(nparts + 1);
+  GK(cudaMemcpy(b1.data(), base1.p, (nparts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  // pass 2
+  GK(cudaMemset(d_flag.p, 0, 2 * sizeof(unsigned long long)));
+  k_agg_pass2<<<g_n, TB>>>(s_ptr.p, s_col.p, n, agg1.p, agg2.p, d_flag.p + 1);
+  unsigned long long left = 0;
+  GK(cudaMemcpy(&left, d_flag.p + 1, sizeof(left), cudaMemcpyDeviceToHost));
+  if (left) return false;  // cannot happen with a symmetric S (header comment); the host's pass 3 handles it
+  GK(cudaGetLastError());
+  GK(cudaDeviceSynchronize());
+  agg2.download(agg_by_gid, (size_t)n);
+  for (int32_t p = 0; p < nparts; ++p) counts[p] = b1[p + 1] - b1[p];
+  if (getenv("PAMG_SETUP_TIMING"))
+    std::fprintf(stderr, "[pamg setup] GPU aggregation: %lld vertices, %lld strong edges, %lld rounds\n", (long long)n, (long long)s_nnz,
+                 (long long)rounds1);
+  return true;
+}
+
 void gpu_spgemm(const Csr& A, const Csr& B, Csr& C) {
   std::unique_ptr<GpuMat> a(gpu_upload(A)), b(gpu_upload(B));
   std::unique_ptr<GpuMat> c(gpu_product(a.get(), b.get()));
