@@ -163,6 +163,33 @@ def cpu_solve_timed(c, nparts, b_parts, reps, threads=None):
     return times, it, hist
 
 
+def other_krylov_drivers(c, nparts, b_parts, own_all, b):
+    """SURVEY 8(f3) record: flexible CG and restarted flexible GMRES through the C ABI on this workload, each against the C
+    oracle's restatement of the same driver (iterations and residual history).  Returns a dict; never raises."""
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import c_oracle
+        co = c_oracle.COracle.from_product_context(c, nparts)
+        rhs = [b[o] for o in own_all]
+        for name, dev, ref in (("fcg", lambda: c.fcg(b_parts, RTOL, MAXITER), lambda: co.pcg(rhs, RTOL, MAXITER, True, flexible=True)),
+                               ("fgmres30", lambda: c.fgmres(b_parts, RTOL, MAXITER, 30, True), lambda: co.fgmres(rhs, RTOL, MAXITER, 30, True))):
+            try:
+                dev()                                   # warm-up (graph capture, basis allocation)
+                x, it, hist, ok = dev()
+                ms = c.stats().solve_ms
+                xr, it_ref, hist_ref = ref()
+                out[name] = dict(iters=int(it), oracle_iters=int(it_ref), iters_match=bool(it == it_ref), converged=bool(ok),
+                                 history_match=bool(len(hist) == len(hist_ref) and np.allclose(hist, hist_ref, rtol=1e-7)),
+                                 device_ms=float(ms))
+            except Exception as e:  # noqa: BLE001
+                out[name] = dict(error=f"{type(e).__name__}: {e}")
+        co.close()
+    except Exception as e:  # noqa: BLE001
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def write_trace(c, part, path):
     """Per-kernel timeline of one resident solve: start-to-start deltas (device globaltimer) of every kernel
     of a PCG iteration, median over the iterations.  Diagnostic only (not part of any reported number)."""
@@ -422,6 +449,8 @@ def measure(workload, args, rank, world, local_rank, steps, warmup, headline):
                          ms_per_step=e2e_ms / steps),
                 gpu_launches=int(launches), clocks=clocks, cpu_baseline=cpu, parity=parity,
                 host_setup_s=round(setup_s, 1), host_setup="rank 0 + shared-memory hand-off" if share else "every rank")
+            if world == 1 and not headline and n <= 3_000_000 and not args.no_cpu_baseline and wl.get("kind") is None:
+                rec["krylov"] = other_krylov_drivers(c, nparts, b_parts, [c.index_maps(0, p)[0] for p in range(nparts)], b)
         finally:   # whatever happens here, the sleeping ranks must be released
             if world > 1:
                 open(flag, "w").close()

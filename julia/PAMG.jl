@@ -182,6 +182,31 @@ function solve!(x::PVector, S::Setup, b::PVector; rtol = 1e-8, maxiter = 200, pr
     (iterations = Int(iters[]), converged = st == 0, residuals = hist[1:iters[]+1])
 end
 
+# flexible AMG-preconditioned CG (pamg_fcg) and restarted flexible GMRES (pamg_fgmres): same result tuple as solve!
+function solve_fcg!(x::PVector, S::Setup, b::PVector; rtol = 1e-8, maxiter = 200)
+    iters = Ref{Int32}(0)
+    hist = zeros(Float64, maxiter + 2)
+    bp, xp = own_ptrs(b, S), own_ptrs(x, S)
+    st = GC.@preserve b x ccall((:pamg_fcg, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Float64, Int32, Ref{Int32}, Ptr{Float64}),
+        S.ctx, bp, xp, rtol, maxiter, iters, hist)
+    st == -5 || check(S.ctx, st)
+    wait(consistent!(x))
+    (iterations = Int(iters[]), converged = st == 0, residuals = hist[1:iters[]+1])
+end
+
+function solve_gmres!(x::PVector, S::Setup, b::PVector; rtol = 1e-8, maxiter = 200, restart = 30, precond = true)
+    iters = Ref{Int32}(0)
+    hist = zeros(Float64, maxiter + 2)
+    bp, xp = own_ptrs(b, S), own_ptrs(x, S)
+    st = GC.@preserve b x ccall((:pamg_fgmres, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Float64, Int32, Int32, Int32, Ref{Int32}, Ptr{Float64}),
+        S.ctx, bp, xp, rtol, maxiter, restart, precond ? 1 : 0, iters, hist)
+    st == -5 || check(S.ctx, st)
+    wait(consistent!(x))
+    (iterations = Int(iters[]), converged = st == 0, residuals = hist[1:iters[]+1])   # residuals: the Arnoldi estimates
+end
+
 function vcycle!(z::PVector, S::Setup, r::PVector)
     rp, zp = own_ptrs(r, S), own_ptrs(z, S)
     GC.@preserve r z check(S.ctx, ccall((:pamg_vcycle, lib), Cint,
