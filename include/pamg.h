@@ -102,6 +102,8 @@ typedef struct {
   double sell_fill[16];   /* stored entries / nnz of A's SELL layout (1.0 when A is not SELL) */
   int32_t fused_halo;     /* 1 when the halo roles run inside the consuming kernels */
   int32_t tail_level;     /* first level of the replicated coarse tail (n_levels - 1: coarsest only) */
+  int32_t value_indexed[16]; /* per level, bit mask 1 A / 2 P / 4 R: the SELL block stores one byte per entry into a dictionary of its
+                             <= 256 distinct fp64 values instead of the values (same products, same order, same bits) */
 } pamg_stats;
 
 void pamg_default_options(pamg_options* o);
@@ -198,6 +200,12 @@ int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double
 int pamg_layout_sell(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
                      int64_t* n_slices, int64_t* stored, int32_t* permuted, int32_t* slice_off, int32_t* col,
                      double* val, int32_t* perm);
+/* value-indexed SELL storage of the same block: *indexed = 1 when it has at most 255 distinct non-zero values (bit patterns), then
+ * dict[256] (dict[0] = +0.0, the padding value; ascending bit pattern behind it; unused entries 0.0) and vidx[stored] with
+ * dict[vidx[k]] == val[k] bit for bit in the layout of pamg_layout_sell.  The device stores such blocks as int32 column +
+ * one byte per entry (kernels.cuh k_spmv_sell_vi); env PAMG_VALUE_INDEX=0 keeps the fp64 values. */
+int pamg_layout_sell_values(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
+                            int32_t* indexed, int64_t* stored, double* dict, uint8_t* vidx);
 int pamg_layout_stream(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t max_rows, int32_t max_entries,
                        int64_t* n_blocks, int32_t* first_row, int32_t* first_entry);
 int pamg_layout_boundary(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int64_t* n_rows, int64_t* n_entries,

@@ -49,6 +49,7 @@ class Stats(C.Structure):
         ("solve_ms", C.c_double), ("vcycle_ms", C.c_double), ("kernel_launches", C.c_int64),
         ("n_levels", C.c_int32), ("format", C.c_int32 * 16), ("lanes", C.c_int32 * 16),
         ("format_p", C.c_int32 * 16), ("format_r", C.c_int32 * 16), ("sell_fill", C.c_double * 16), ("fused_halo", C.c_int32), ("tail_level", C.c_int32),
+        ("value_indexed", C.c_int32 * 16),
     ]
 
 
@@ -81,6 +82,7 @@ PROTOTYPES = {
     "pamg_coarse_upload": [_ctx, C.c_int64, _f64p],
     "pamg_hierarchy_end": [_ctx],
     "pamg_layout_sell": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p, _i32p, _i32p, _i32p, _f64p, _i32p],
+    "pamg_layout_sell_values": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i64p, _f64p, _P(C.c_uint8)],
     "pamg_layout_stream": [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64p, _i32p, _i32p],
     "pamg_layout_boundary": [_ctx, C.c_int32, C.c_int32, C.c_int32, _i64p, _i64p, _i32p, _i32p, _i32p, _i32p, _i32p, _f64p,
                              _P(C.c_uint8)],
@@ -369,6 +371,17 @@ class Context:
                                            C.byref(pm), _ptr(off, C.c_int32), _ptr(col, C.c_int32), _ptr(val, C.c_double),
                                            _ptr(perm, C.c_int32)))
         return dict(slice_off=off, col=col, val=val, perm=perm, permuted=bool(pm.value), C=rows_per_slice)
+
+    def layout_sell_values(self, level, part, which, rows_per_slice=64, sigma=1):
+        """(dict[256], vidx[stored]) of the value-indexed SELL storage, or None when the block has more than 255 distinct values."""
+        ix, st = C.c_int32(), C.c_int64()
+        self._ck(self.lib.pamg_layout_sell_values(self._h, level, part, which, rows_per_slice, sigma, C.byref(ix), C.byref(st), None, None))
+        if not ix.value:
+            return None
+        d, v = np.zeros(256), np.zeros(st.value, np.uint8)
+        self._ck(self.lib.pamg_layout_sell_values(self._h, level, part, which, rows_per_slice, sigma, C.byref(ix), C.byref(st),
+                                                  _ptr(d, C.c_double), _ptr(v, C.c_uint8)))
+        return d, v
 
     def layout_stream(self, level, part, which, max_rows=1024, max_entries=3069):
         nb = C.c_int64()

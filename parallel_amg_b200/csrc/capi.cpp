@@ -336,6 +336,28 @@ int pamg_layout_sell(pamg_ctx* c, int32_t level, int32_t part, int32_t which, in
   });
 }
 
+int pamg_layout_sell_values(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
+                            int32_t* indexed, int64_t* stored, double* dict, uint8_t* vidx) {
+  return guard(c, [&] {
+    const PartLevel& pl = part_level(c, level, part);
+    need(pl.full, "this part was loaded as metadata only (pamg_hierarchy_load keep_part)");
+    need(which == PAMG_A_OO || which == PAMG_P_OO || which == PAMG_R_OO, "SELL applies to own-own blocks");
+    need(rows_per_slice >= 1 && rows_per_slice <= 1024 && indexed && stored, "bad arguments");
+    SellHost sh;
+    const bool ok = value_dictionary(pl.blk[which], sh.dict);
+    *indexed = ok ? 1 : 0;
+    sell_layout(pl.blk[which], rows_per_slice, sigma, sh, ok && vidx != nullptr);
+    *stored = (int64_t)sh.off[sh.off.size() - 1] * rows_per_slice;
+    if (!ok) return PAMG_OK;
+    if (dict) std::memcpy(dict, sh.dict.data(), 256 * sizeof(double));
+    if (vidx) {
+      sell_value_index(sh);
+      std::memcpy(vidx, sh.vidx.data(), (size_t)*stored);
+    }
+    return PAMG_OK;
+  });
+}
+
 int pamg_layout_stream(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t max_rows, int32_t max_entries,
                        int64_t* n_blocks, int32_t* first_row, int32_t* first_entry) {
   return guard(c, [&] {

@@ -80,6 +80,11 @@ struct DevCsr {
   bool sell_perm = false;
   double sell_fill = 1.0;  // stored entries / nnz
   bool short_rows = false; // no row has more than 8 entries (prolongators): eligible for the short-row instantiations
+  // value-indexed SELL (RPT = 2 only): one byte per stored entry into a dictionary of the <= 256 distinct values
+  DBuf<uint8_t> sl_vidx;
+  DBuf<double> sl_dict;
+  bool sell_vi = false;
+  SellViView viview() const { return SellViView{sl_off.p, sl_col.p, sl_vidx.p, sl_dict.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
   CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
   StreamView sview() const { return StreamView{blk.p, ptr.p, col.p, val.p, nrows, nblocks}; }
   SellView slview() const { return SellView{sl_off.p, sl_col.p, sl_val.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
@@ -186,6 +191,7 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
   d.stream = false;
   d.nblocks = 0;
   d.sell_rpt = 0;
+  d.sell_vi = false;
   d.short_rows = false;
   if (!m.ptr.empty()) {
     int64_t mx = 0;
@@ -252,6 +258,16 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
       d.sl_off.upload(sh.off);
       d.sl_col.upload(sh.col);
       d.sl_val.upload(sh.val);
+      d.sell_vi = false;
+      {  // few distinct values (stencil matrices, their prolongators): value-indexed storage, 5 instead of 12 bytes per entry
+        const char* e = getenv("PAMG_VALUE_INDEX");
+        if (rpt == 2 && !(e && atoi(e) == 0) && value_dictionary(m, sh.dict)) {
+          sell_value_index(sh);
+          d.sl_vidx.upload(sh.vidx);
+          d.sl_dict.upload(sh.dict);
+          d.sell_vi = true;
+        }
+      }
       d.sell_perm = sh.permuted;
       if (sh.permuted) d.sl_perm.upload(sh.perm);
       d.nslices = (int)sh.off.size() - 1;
@@ -497,6 +513,7 @@ struct Engine::Impl {
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
   int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
+  int vi_variant = 0;       // value-indexed SELL kernel: 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM> (env PAMG_VI_VARIANT)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
   bool counting = true;
@@ -666,10 +683,17 @@ void launch_stream(int mode, bool dot, bool long_rows, StreamView A, const Launc
 // try_unified: fused launch of one part per GPU -- run without role CTAs when every CTA's share of the boundary rows fits
 // (kernels.cuh "Unified CTA roles"); *was_unified reports the decision.
 void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, SellView A, LaunchArgs L, bool try_unified,
-                 int unified_mode, bool* was_unified) {
+                 int unified_mode, bool* was_unified, const SellViView* vi = nullptr, int vi_variant = 0) {
   dispatch_mode(mode, dot, [&](auto md, auto dt) {
     constexpr int MD = decltype(md)::value;
     constexpr bool DT = decltype(dt)::value;
+    if (vi && rpt == 2 && !try_unified) {  // value-indexed operator: its own kernel (the experimental variants below do not apply)
+      *was_unified = false;
+      using KernVi = void (*)(SellViView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
+      KernVi kv = vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2> : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
+      kv<<<main_grid(L, (const void*)kv), BLOCK, 0, L.s>>>(*vi, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
+      return;
+    }
     using Kern = void (*)(SellView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
     Kern k = rpt == 2 ? (Kern)k_spmv_sell<2, MD, DT> : (Kern)k_spmv_sell<1, MD, DT>;
     if constexpr (MD == M_ADD && !DT) {
@@ -811,9 +835,11 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     }
     L.grid = std::max(n_main, 1);
     bool was_unified = false;
+    SellViView viv{};
+    if (m.sell_vi) viv = m.viview();
     if (m.sell_rpt)
       launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
-                  try_unified, I.unified_mode, &was_unified);
+                  try_unified, I.unified_mode, &was_unified, m.sell_vi ? &viv : nullptr, I.vi_variant);
     else if (m.stream)
       launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
@@ -821,7 +847,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     if (I.naming) {
       static const char* MODES[] = {"mul", "resid", "jacobi", "add", "restrict", "cheb"};
       static const char* OPS[] = {"A", "P", "R"};
-      I.names.push_back(std::string(m.sell_rpt ? "sell " : m.stream ? "stream " : "csr ") + MODES[op.mode] + (op.dot ? "+dot " : " ") +
+      I.names.push_back(std::string(m.sell_rpt ? (m.sell_vi && !was_unified ? "sell-vi " : "sell ") : m.stream ? "stream " : "csr ") + MODES[op.mode] + (op.dot ? "+dot " : " ") +
                         OPS[wsel] + std::to_string(l) + (I.tail_mode ? " tail" : "") + (fh.n_pack ? " +pack" : "") +
                         (fh.n_bnd ? " +bnd" : "") + (was_unified ? " uni" : ""));
       I.naming = false;
@@ -898,6 +924,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   I.have_ipc.assign(I.nparts, 0);
   const pamg_options& o = h->opts;
   if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
+  if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(1, atoi(vv)));
 
   // global decisions (identical in every process because the metadata is replicated)
   I.need_halo_A.assign(I.L, 0);
@@ -2637,6 +2664,11 @@ void Engine::get_stats(pamg_stats* s) {
     s->format_r[l] = have && l + 1 < I.L ? fmt_of(I.P(0).lev[l]->blk[PAMG_R_OO]) : 0;
     s->lanes[l] = have ? I.P(0).lev[l]->blk[PAMG_A_OO].lanes : 0;
     s->sell_fill[l] = have ? I.P(0).lev[l]->blk[PAMG_A_OO].sell_fill : 1.0;
+    s->value_indexed[l] = 0;
+    if (have) {
+      const LevelDev& ld = *I.P(0).lev[l];
+      s->value_indexed[l] = (ld.blk[PAMG_A_OO].sell_vi ? 1 : 0) | (ld.blk[PAMG_P_OO].sell_vi ? 2 : 0) | (ld.blk[PAMG_R_OO].sell_vi ? 4 : 0);
+    }
   }
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <climits>
+#include <cstring>
 #include <cstdint>
 #include <stdexcept>
 #include <utility>
@@ -22,7 +23,82 @@ struct SellHost {
   std::vector<double> val;
   bool permuted = false;
   double fill = 1.0;  // stored entries / nnz
+  // value-indexed storage (kernels.cuh k_spmv_sell_vi): dict = the distinct values (dict[0] = +0.0, the padding value; 256
+  // entries, unused ones 0.0), vidx = one byte per stored entry, same layout as col.  Empty when the operator has more
+  // than 255 distinct non-padding values.
+  std::vector<double> dict;
+  std::vector<uint8_t> vidx;
 };
+
+// Distinct values of m by BIT PATTERN (-0.0 and +0.0 are different entries: the products keep their sign), ascending by
+// pattern behind dict[0] = +0.0.  Returns false as soon as more than 255 are seen (then `dict` is empty).
+inline bool value_dictionary(const LocalCsr& m, std::vector<double>& dict) {
+  dict.clear();
+  const int64_t nnz = m.nnz();
+  auto bits = [](double v) {
+    uint64_t b;
+    std::memcpy(&b, &v, sizeof(b));
+    return b;
+  };
+  std::vector<uint64_t> all;
+  bool too_many = false;
+#pragma omp parallel
+  {
+    std::vector<uint64_t> mine;  // sorted, tiny
+    uint64_t last = ~0ull;       // no finite double: a NaN pattern that never occurs as a stored value twice in a row first
+    bool have_last = false;
+#pragma omp for schedule(static)
+    for (int64_t k = 0; k < nnz; ++k) {
+      if (too_many) continue;
+      const uint64_t b = bits(m.val[k]);
+      if (have_last && b == last) continue;
+      last = b;
+      have_last = true;
+      auto it = std::lower_bound(mine.begin(), mine.end(), b);
+      if (it == mine.end() || *it != b) {
+        mine.insert(it, b);
+        if (mine.size() > 255) {
+#pragma omp atomic write
+          too_many = true;
+        }
+      }
+    }
+#pragma omp critical
+    all.insert(all.end(), mine.begin(), mine.end());
+  }
+  if (too_many) return false;
+  std::sort(all.begin(), all.end());
+  all.erase(std::unique(all.begin(), all.end()), all.end());
+  all.erase(std::remove(all.begin(), all.end(), (uint64_t)0), all.end());  // +0.0 is dict[0] anyway
+  if (all.size() > 255) return false;
+  dict.assign(256, 0.0);
+  for (size_t i = 0; i < all.size(); ++i) std::memcpy(&dict[i + 1], &all[i], sizeof(double));
+  return true;
+}
+
+// vidx of an already filled SELL layout; dict from value_dictionary (sorted by bit pattern behind dict[0])
+inline void sell_value_index(SellHost& sh, int n_distinct_hint = 256) {
+  (void)n_distinct_hint;
+  std::vector<uint64_t> key(256, 0);
+  int nd = 1;
+  for (int i = 1; i < 256; ++i) {
+    uint64_t b;
+    std::memcpy(&b, &sh.dict[i], sizeof(b));
+    if (b == 0) break;  // unused tail (a stored +0.0 maps to entry 0)
+    key[i] = b;
+    nd = i + 1;
+  }
+  const int64_t stored = (int64_t)sh.val.size();
+  sh.vidx.assign(sh.val.size(), 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < stored; ++k) {
+    uint64_t b;
+    std::memcpy(&b, &sh.val[k], sizeof(b));
+    if (b == 0) continue;
+    const auto it = std::lower_bound(key.begin() + 1, key.begin() + nd, b);
+    sh.vidx[k] = (uint8_t)(it - key.begin());
+  }
+}
 
 inline void sell_layout(const LocalCsr& m, int C, int sigma, SellHost& out, bool fill_arrays) {
   const int64_t nr = m.nrows;

@@ -93,10 +93,10 @@ GpuMat* gpu_transpose(const GpuMat* A);                                         
 // the greedy 3-pass aggregation of ALL parts on the device, bit-identical to the host's aggregate_part.
 // A: the level matrix (or the node graph) on the device; owner[g]; pos[g] = first row of the owner part + own-local id
 // (part-major position); part_off[nparts + 1]; agg_by_gid[g] = aggregate id inside the owner part; counts[p] = aggregates
-// of part p.  Returns false (nothing written) when the strength graph is not symmetric or the dependency chain is too long:
-// the caller then walks the rows on the host.
+// of part p.  Returns false (nothing written) when the strength graph is not symmetric, the dependency chain is too long, or
+// (force == false) the level is one the host's walk finishes sooner (small, or long rows): the caller then walks the rows.
 bool gpu_aggregate(const GpuMat* A, const int32_t* owner, const int32_t* pos, const int64_t* part_off, int32_t nparts, double eps,
-                   int32_t* agg_by_gid, int64_t* counts);
+                   bool force, int32_t* agg_by_gid, int64_t* counts);
 void gpu_setup_begin();  // pinned staging buffers for the transfers of one setup
 void gpu_setup_end();
 

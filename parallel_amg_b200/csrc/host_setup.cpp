@@ -554,11 +554,11 @@ static void aggregate_all(const Csr& M, const GpuMat* dM, const std::vector<int3
       std::vector<int32_t> pos(n);
 #pragma omp parallel for schedule(static)
       for (int64_t g = 0; g < n; ++g) pos[g] = (int32_t)(part_off[owner[g]] + oi.lid[g]);
-      if (gpu_aggregate(dM, owner.data(), pos.data(), part_off.data(), nparts, eps, agg_gid.data(), counts.data())) {
+      if (gpu_aggregate(dM, owner.data(), pos.data(), part_off.data(), nparts, eps, mode == 2, agg_gid.data(), counts.data())) {
         *on_gpu = true;
         return;
       }
-      why = "the strength graph is not symmetric or its dependency chain is too long";
+      why = "the strength graph is not symmetric, or its dependency chain is too long";
     } catch (const std::exception& ex) {
       why = ex.what();
       std::fprintf(stderr, "[pamg setup] GPU aggregation failed (%s): falling back to the host\n", ex.what());

@@ -1015,6 +1015,106 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell(SellView A, const dou
   if (DOT) dot_finish(s_acc[threadIdx.x], partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Value-indexed SELL (RPT = 2).  An operator with at most 256 DISTINCT values -- the 7-point Poisson matrix has two, its
+// smoothed-aggregation prolongator and restriction nine -- is stored as int32 columns + one byte per entry that indexes a
+// dictionary of the distinct fp64 values (CSR-VI, Kourtis et al.): 5 bytes per entry instead of 12 cross the HBM pins.  The
+// dictionary (<= 2 KB) sits in shared memory; every product is __dmul_rn(dict[i], x[c]) with the ORIGINAL double, summed in
+// the same order, so results are bit-identical to the fp64-valued kernel.  Layout of the indices = layout of the columns
+// (entry j of slot q at (slice_off[sl] + j) * 64 + q): a lane reads its two rows' indices with one 16-bit load.
+// A kernel of its own so that the fp64-valued production instantiations keep their registers and load schedule.
+// ---------------------------------------------------------------------------------------------
+struct SellViView {
+  const int32_t* slice_off;
+  const int32_t* col;
+  const uint8_t* vidx;   // [slice_off[nslices] * 64] dictionary index per stored entry (padding -> the entry holding 0.0)
+  const double* dict;    // [256]
+  const int32_t* perm;
+  int32_t nrows, nslices;
+};
+
+template <int MODE, bool DOT, int U = 4, int MINB = 3>
+__global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi(SellViView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
+                                                         double* partials, RedCtx rc, int publish, int red_slot) {
+  if (st->done) return;
+  trace_mark(st);
+  const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
+  const int bid = (int)blockIdx.x - fh.n_pack - (fh.bnd_first ? fh.n_bnd : 0);
+  const int b0 = fh.n_pack + (fh.bnd_first ? 0 : n_main);  // first boundary CTA
+  if ((int)blockIdx.x < fh.n_pack || ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + fh.n_bnd)) {  // halo roles
+    double racc = 0.0;
+    if ((int)blockIdx.x < fh.n_pack)
+      pack_role(fh, st, blockIdx.x);
+    else
+      racc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - b0);
+    if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+    return;
+  }
+  __shared__ double s_dict[256];
+  __shared__ double s_acc[DOT ? BLOCK : 1];
+  s_dict[threadIdx.x] = A.dict[threadIdx.x];  // BLOCK == 256
+  if (DOT) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = BLOCK / 32;
+  for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
+    const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
+    const int slot0 = sl * 64 + lane * 2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int slot = slot0 + k;
+      if (slot < A.nrows) {
+        const int r = A.perm ? A.perm[slot] : slot;
+        if (fh.skip) asm volatile("prefetch.global.L1 [%0];" ::"l"(fh.skip + r));
+        if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) prefetch_l1(a.in0 + r);
+        if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) prefetch_l1(a.w + r);
+        if (MODE == M_CHEB && a.aux) prefetch_l1(a.aux + r);
+        if (DOT && a.dotv != a.in0) prefetch_l1(a.dotv + r);
+      }
+    }
+    double s0 = 0.0, s1 = 0.0;
+    const int2* __restrict__ cj = reinterpret_cast<const int2*>(A.col) + (size_t)o0 * 32 + lane;
+    const unsigned short* __restrict__ ij = reinterpret_cast<const unsigned short*>(A.vidx) + (size_t)o0 * 32 + lane;
+#pragma unroll 1
+    for (int j0 = 0; j0 < w; j0 += U, cj += U * 32, ij += U * 32) {
+      int2 c[U];
+      unsigned short iv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) {
+          c[u] = __ldcs(cj + u * 32);
+          iv[u] = __ldcs(ij + u * 32);
+        }
+      double xv[U][2];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) {
+          xv[u][0] = x[c[u].x];
+          xv[u][1] = x[c[u].y];
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) {
+          s0 = __dadd_rn(s0, __dmul_rn(s_dict[iv[u] & 0xffu], xv[u][0]));
+          s1 = __dadd_rn(s1, __dmul_rn(s_dict[iv[u] >> 8], xv[u][1]));
+        }
+    }
+    double contrib = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int slot = slot0 + k;
+      if (slot < A.nrows) {
+        const int r = A.perm ? A.perm[slot] : slot;
+        if (fh.skip && fh.skip[r]) continue;
+        const double res = apply_epilogue<MODE, false>(a, r, k ? s1 : s0);
+        if (DOT) contrib += a.dotv[r] * res;
+      }
+    }
+    if (DOT) s_acc[threadIdx.x] += contrib;
+  }
+  if (DOT) dot_finish(s_acc[threadIdx.x], partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+}
+
 // The unified-role kernel (RPT = 2, U = 4).  A kernel of its own: with the role code inlined into k_spmv_sell, ptxas gave
 // three of the production instantiations 80 instead of 72 registers and a worse load schedule (L0 Jacobi +5 %, P0 2.2x).
 template <int MODE, bool DOT>

@@ -596,55 +596,88 @@ __global__ void k_sym_check(const int64_t* __restrict__ sp, const int32_t* __res
   }
 }
 
-// one round of the fixed point (distance 2); *left = vertices still undecided after it
-__global__ void k_mis_round(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, int64_t n, unsigned char* state,
-                            int32_t* __restrict__ blocker, unsigned long long* left) {
-  unsigned long long mine = 0;
-  for (int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TB) {
+// The fixed point is event driven.  A work list holds the vertices that may be decidable; a round is two launches:
+//   decide  every listed vertex looks at its earlier vertices within distance 2: a ROOT among them -> NOT; none undecided ->
+//           ROOT; else it records the LARGEST undecided one as its blocker (the front moves in id order, so that one goes
+//           last) and sleeps.  Reads of `state` may be stale inside the launch: that only delays a decision.
+//   wake    (all states of the round are final now) a listed vertex that is still undecided re-queues itself if its blocker
+//           was decided meanwhile; a vertex decided in this round queues every later vertex within distance 2 that sleeps
+//           on it.  `stamp` keeps a vertex from entering a list twice.
+// Invariant: an undecided vertex is listed or sleeps on an undecided blocker; the smallest undecided vertex has no
+// undecided earlier vertex, so it is listed: an empty list means everything is decided.  One warp per listed vertex: lane l
+// walks the neighbourhoods of the neighbours l, l + 32, ... (rows of 7 and rows of 80 entries get the same short chain).
+template <class F>
+__device__ __forceinline__ void scan_dist2(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, int64_t i, int lane, F&& f) {
+  const int64_t e0 = sp[i + 1];
+  for (int64_t q = sp[i] + lane; q < e0; q += 32) {
+    const int32_t v = sc[q];
+    f(v);
+    const int64_t e1 = sp[v + 1];
+    for (int64_t q2 = sp[v]; q2 < e1; ++q2) f(sc[q2]);
+  }
+}
+
+__global__ void k_agg_decide(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, const int32_t* __restrict__ list,
+                             const unsigned* __restrict__ cnt_ptr, int64_t cnt_fixed, unsigned char* state, int32_t* __restrict__ blocker) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (TB / 32);
+  const int64_t cnt = list ? (int64_t)*cnt_ptr : cnt_fixed;
+  for (int64_t w = (int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5); w < cnt; w += nw) {
+    const int64_t i = list ? (int64_t)list[w] : w;
     if (ld_state(state + i) != ST_U) continue;
-    const int32_t b = blocker[i];
-    if (b >= 0 && ld_state(state + b) == ST_U) {
-      ++mine;
-      continue;
-    }
     bool has_root = false;
     int32_t maxu = -1;
-    const int64_t e0 = sp[i + 1];
-    for (int64_t q = sp[i]; q < e0 && !has_root; ++q) {
-      const int32_t v = sc[q];
-      if ((int64_t)v < i) {
-        const unsigned char s = ld_state(state + v);
+    scan_dist2(sp, sc, i, lane, [&](int32_t k) {
+      if ((int64_t)k < i) {
+        const unsigned char s = ld_state(state + k);
         if (s == ST_ROOT)
           has_root = true;
         else if (s == ST_U)
-          maxu = max(maxu, v);
+          maxu = max(maxu, k);
       }
-      {
-        const int64_t e1 = sp[v + 1];
-        for (int64_t q2 = sp[v]; q2 < e1 && !has_root; ++q2) {
-          const int32_t k = sc[q2];
-          if ((int64_t)k < i) {
-            const unsigned char s = ld_state(state + k);
-            if (s == ST_ROOT)
-              has_root = true;
-            else if (s == ST_U)
-              maxu = max(maxu, k);
-          }
-        }
-      }
-    }
-    if (has_root) {
-      state[i] = ST_NOT;
-    } else if (maxu < 0) {
-      state[i] = ST_ROOT;
-    } else {
-      blocker[i] = maxu;
-      ++mine;
+    });
+    has_root = __any_sync(0xffffffffu, has_root);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxu = max(maxu, __shfl_xor_sync(0xffffffffu, maxu, o));
+    if (lane == 0) {
+      if (has_root)
+        state[i] = ST_NOT;
+      else if (maxu < 0)
+        state[i] = ST_ROOT;
+      else
+        blocker[i] = maxu;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
-  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(left, mine);
+}
+
+__device__ __forceinline__ void agg_push(int32_t j, int32_t* stamp, int32_t tag, int32_t* list_out, unsigned* cnt_out) {
+  if (atomicExch(stamp + j, tag) != tag) list_out[atomicAdd(cnt_out, 1u)] = j;  // at most n entries: one per vertex and list
+}
+
+__global__ void k_agg_wake(const int64_t* __restrict__ sp, const int32_t* __restrict__ sc, const int32_t* __restrict__ list,
+                           const unsigned* __restrict__ cnt_ptr, int64_t cnt_fixed, const unsigned char* state,
+                           const int32_t* __restrict__ blocker, int32_t* stamp, int32_t tag, int32_t* __restrict__ list_out,
+                           unsigned* cnt_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (TB / 32);
+  const int64_t cnt = list ? (int64_t)*cnt_ptr : cnt_fixed;
+  for (int64_t w = (int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5); w < cnt; w += nw) {
+    const int64_t i = list ? (int64_t)list[w] : w;
+    if (ld_state(state + i) == ST_U) {  // asleep: unless its blocker went in this very round
+      if (lane == 0 && ld_state(state + blocker[i]) != ST_U) agg_push((int32_t)i, stamp, tag, list_out, cnt_out);
+      continue;
+    }
+    scan_dist2(sp, sc, i, lane, [&](int32_t k) {
+      if ((int64_t)k > i && ld_state(state + k) == ST_U && blocker[k] == (int32_t)i) agg_push(k, stamp, tag, list_out, cnt_out);
+    });
+  }
+}
+
+__global__ void k_count_undecided(const unsigned char* __restrict__ state, int64_t n, unsigned long long* out) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const bool u = i < n && state[i] == ST_U;
+  const unsigned m = __ballot_sync(0xffffffffu, u);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 
 // flags[pos[g]] = 1 for the roots (part-major order: its exclusive scan ranks the roots inside every part); flags[n] = 0
@@ -690,37 +723,62 @@ __global__ void k_agg_pass2(const int64_t* __restrict__ sp, const int32_t* __res
   agg2[v] = a;
   if (a == -1) atomicAdd(left, 1ull);
 }
-// runs the fixed point to the end; false: gave up (a dependency chain longer than max_rounds, e.g. a 1-D problem)
+// runs the fixed point to the end; false: gave up (a dependency chain longer than max_rounds) or something is left undecided
 bool mis_rounds(const int64_t* sp, const int32_t* sc, int64_t n, unsigned char* state, int32_t* blocker, int64_t max_rounds, int64_t* rounds_out) {
-  constexpr int BATCH = 48;
-  Buf<unsigned long long> d_left;
-  d_left.alloc(BATCH);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + TB - 1) / TB, 148 * 16));
-  int64_t rounds = 0;
+  constexpr int CHECK_EVERY = 32;
+  Buf<int32_t> list[2], stamp;
+  Buf<unsigned> cnt;
+  list[0].alloc(n);
+  list[1].alloc(n);
+  stamp.alloc(n);
+  cnt.alloc(2);
+  GK(cudaMemset(stamp.p, 0xff, n * sizeof(int32_t)));
+  GK(cudaMemset(cnt.p, 0, 2 * sizeof(unsigned)));
+  const int wpb = TB / 32;
+  const int grid0 = (int)std::max<int64_t>(1, std::min<int64_t>((n + wpb - 1) / wpb, (int64_t)1 << 20));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + wpb - 1) / wpb, 148 * 16));
+  int64_t round = 0;
   while (true) {
-    GK(cudaMemset(d_left.p, 0, BATCH * sizeof(unsigned long long)));
-    for (int r = 0; r < BATCH; ++r) k_mis_round<<<grid, TB>>>(sp, sc, n, state, blocker, d_left.p + r);
-    GK(cudaGetLastError());
-    rounds += BATCH;
-    unsigned long long left = 0;
-    GK(cudaMemcpy(&left, d_left.p + (BATCH - 1), sizeof(left), cudaMemcpyDeviceToHost));
-    if (left == 0) break;
-    if (rounds > max_rounds) return false;
+    // list of round r: all vertices (r == 0), else list[r & 1] with cnt[r & 1] entries; round r fills list[(r + 1) & 1]
+    const int32_t* in = round == 0 ? nullptr : list[round & 1].p;
+    const unsigned* cin = cnt.p + (round & 1);
+    unsigned* cout = cnt.p + ((round + 1) & 1);
+    k_agg_decide<<<round == 0 ? grid0 : grid, TB>>>(sp, sc, in, cin, n, state, blocker);
+    GK(cudaMemsetAsync(cout, 0, sizeof(unsigned)));
+    k_agg_wake<<<round == 0 ? grid0 : grid, TB>>>(sp, sc, in, cin, n, state, blocker, stamp.p, (int32_t)(round & 0x3fffffff), list[(round + 1) & 1].p, cout);
+    ++round;
+    if (round % CHECK_EVERY == 0) {
+      GK(cudaGetLastError());
+      unsigned next = 0;
+      GK(cudaMemcpy(&next, cout, sizeof(next), cudaMemcpyDeviceToHost));
+      if (next == 0) break;
+      if (round > max_rounds) return false;
+    }
   }
-  if (rounds_out) *rounds_out = rounds;
-  return true;
+  Buf<unsigned long long> left;
+  left.alloc(1);
+  GK(cudaMemset(left.p, 0, sizeof(unsigned long long)));
+  k_count_undecided<<<(int)((n + TB - 1) / TB), TB>>>(state, n, left.p);
+  unsigned long long l = 0;
+  GK(cudaMemcpy(&l, left.p, sizeof(l), cudaMemcpyDeviceToHost));
+  if (rounds_out) *rounds_out = round;
+  return l == 0;
 }
 
 }  // namespace
 
 bool gpu_aggregate(const GpuMat* A, const int32_t* owner, const int32_t* pos, const int64_t* part_off, int32_t nparts, double eps,
-                   int32_t* agg_by_gid, int64_t* counts) {
+                   bool force, int32_t* agg_by_gid, int64_t* counts) {
   const int64_t n = A->nrows;
   if (n == 0) {
     for (int32_t p = 0; p < nparts; ++p) counts[p] = 0;
     return true;
   }
   if (n >= ((int64_t)1 << 31) - 1) return false;
+  // Where it pays (B200, profiles/r03_setup_timing.txt): the fixed point needs ~1500-4000 rounds whatever the size, so a
+  // small level or one with long rows (Galerkin matrices: 30-70 strong neighbours, 900-4900 vertices within distance 2) is
+  // done sooner by the host's single walk.  force: tests (PAMG_GPU_AGG=2).
+  if (!force && (n < 1000000 || A->nnz > 12 * n)) return false;
   const int g_n = (int)((n + TB - 1) / TB), g_n1 = (int)((n + 1 + TB - 1) / TB);
   Buf<int32_t> d_owner, d_pos;
   d_owner.upload(owner, (size_t)n);

@@ -58,6 +58,9 @@ ENVS = {
     "auto-psig1024": dict(PAMG_P_SIGMA="1024"),
     "auto-rsig4096": dict(PAMG_R_SIGMA="4096"),
     "auto-sort1.1": dict(PAMG_SELL_SORT_FILL="1.1"),
+    "auto-novi": dict(PAMG_VALUE_INDEX="0"),       # fp64 values everywhere (round-2 kernels)
+    "auto-vi1": dict(PAMG_VI_VARIANT="1"),         # value-indexed kernel <U 8, 2 CTAs/SM>
+    "auto-vi-nosort": dict(PAMG_SELL_SORT_FILL="9"),
     "auto-pf1": dict(PAMG_SELL_PF="1"),
     "auto-pf3": dict(PAMG_SELL_PF="3"),
     "auto-pf5": dict(PAMG_SELL_PF="5"),
@@ -73,7 +76,7 @@ else:
     CONFIGS = {k: v for k, v in CONFIGS.items() if k not in ENVS}
 res = {}
 for name, kw in CONFIGS.items():
-    for k in ("PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW", "PAMG_STREAM_LONG", "PAMG_P_SIGMA", "PAMG_R_SIGMA", "PAMG_SELL_PF"):
+    for k in ("PAMG_VALUE_INDEX", "PAMG_VI_VARIANT", "PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW", "PAMG_STREAM_LONG", "PAMG_P_SIGMA", "PAMG_R_SIGMA", "PAMG_SELL_PF"):
         os.environ.pop(k, None)
     os.environ.update(ENVS.get(name, {}))
     c.set_kernel_options(**kw)
@@ -101,6 +104,7 @@ for name, kw in CONFIGS.items():
     except Exception:
         pass
     row["fill"] = [round(st.sell_fill[l], 3) for l in range(c.num_levels())]
+    row["value_indexed"] = [int(st.value_indexed[l]) for l in range(c.num_levels())]
     res[name] = row
     print(name, json.dumps(row), flush=True)
 if out:

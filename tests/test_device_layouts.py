@@ -112,3 +112,54 @@ def test_boundary_rows_are_the_rows_with_ghost_columns(ctx):
             assert np.array_equal(lay["val"][a:m], oo.data[oo.indptr[r]:oo.indptr[r + 1]])
             assert np.array_equal(lay["col"][m:b], ix[ip[r]:ip[r + 1]])
             assert np.array_equal(lay["val"][m:b], d[ip[r]:ip[r + 1]])
+
+
+@pytest.mark.parametrize("C,sigma", [(64, 1), (64, 256)])
+def test_value_indexed_sell_storage(ctx, C, sigma):
+    """kernels.cuh k_spmv_sell_vi reads dict[vidx[k]] instead of val[k]: the dictionary must reproduce every stored value BIT FOR BIT
+    (padding -> entry 0 = +0.0), hold <= 255 distinct non-zero patterns in ascending pattern order, and blocks with more distinct values
+    (the Galerkin matrices of the coarse levels) must be reported as not indexable."""
+    seen_yes = seen_no = 0
+    for l, p, which in blocks(ctx):
+        lay = ctx.layout_sell(l, p, which, C, sigma)
+        vi = ctx.layout_sell_values(l, p, which, C, sigma)
+        vals = ctx.block(l, p, which)[2]
+        distinct = np.unique(vals.view(np.uint64))
+        distinct = distinct[distinct != 0]
+        if len(distinct) > 255:
+            assert vi is None
+            seen_no += 1
+            continue
+        seen_yes += 1
+        assert vi is not None
+        d, idx = vi
+        assert len(idx) == len(lay["val"])
+        assert np.array_equal(d[idx].view(np.uint64), lay["val"].view(np.uint64))      # bit-identical values, padding included
+        assert d.view(np.uint64)[0] == 0
+        used = d.view(np.uint64)[1:1 + len(distinct)]
+        assert np.array_equal(used, distinct) and np.all(d.view(np.uint64)[1 + len(distinct):] == 0)
+    assert seen_yes >= 3 and seen_no >= 1      # level 0 of Poisson has 2 / 9 / 9 distinct values; level 1 has hundreds
+
+
+def test_value_dictionary_keeps_signed_zero_and_counts_exactly():
+    """-0.0 is a value of its own (its products keep their sign); exactly 255 distinct non-zero values still fit, 256 do not."""
+    for ndist, expect in ((255, True), (256, False)):
+        n = 600
+        off = np.ones(n - 1)                                                   # distinct patterns: 1.0, 2 .. k, -0.0, the diagonal = k + 2
+        k = ndist - 2
+        off[:k - 1] = np.arange(2, k + 1, dtype=np.float64)
+        off[300] = -0.0
+        i = np.arange(n - 1)
+        A = sp.coo_matrix((np.concatenate([off, np.full(n, 1000.0), off]), (np.concatenate([i + 1, np.arange(n), i]),
+                                                                            np.concatenate([i, np.arange(n), i + 1]))), shape=(n, n)).tocsr()
+        A.sort_indices()                                                       # explicit (signed) zeros are kept
+        c = L.Context(1)
+        c.set_matrix_global(A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64), np.zeros(n, np.int32))
+        c.setup(c.default_options(coarse_size=10 ** 6))                      # single level: the block is the matrix
+        vi = c.layout_sell_values(0, 0, L.A_OO, 64, 1)
+        assert (vi is not None) == expect
+        if expect:
+            d, idx = vi
+            lay = c.layout_sell(0, 0, L.A_OO, 64, 1)
+            assert np.array_equal(d[idx].view(np.uint64), lay["val"].view(np.uint64))
+            assert (d.view(np.uint64) == np.float64(-0.0).view(np.uint64)).sum() == 1

@@ -450,3 +450,57 @@ def test_fgmres_nonsymmetric_operator():
     for d, v in zip(lev["parts"], x):
         xg[d["own_to_global"]] = v
     assert np.linalg.norm(rhs - A @ xg) <= 1.001e-8 * np.linalg.norm(rhs)
+
+
+# ---- value-indexed SELL storage (kernels.cuh k_spmv_sell_vi) ---------------------------------------------------------------------
+@pytest.mark.parametrize("dims,pp", [((28, 28, 28), (1, 1, 1)), ((33, 31, 17), (3, 2, 1)), ((200, 200), (2, 2))])
+@pytest.mark.parametrize("fmt", ["sell2", "sell2-sorted"])
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_value_indexed_sell_is_bit_identical_to_fp64_values(dims, pp, fmt, variant, monkeypatch):
+    """An operator with <= 255 distinct values is stored as columns + one byte per entry; every kernel mode must give the SAME BITS as
+    the fp64-valued SELL kernels (same products, same order): all level operators, smoothers, the cycle, the PCG history."""
+    monkeypatch.setenv("PAMG_VI_VARIANT", variant)
+    monkeypatch.setenv("PAMG_VALUE_INDEX", "1")
+    A, h, c = make(dims, pp, None, **FORMATS[fmt])
+    assert c.stats().value_indexed[0] == 7, "level 0 of Poisson (2 / 9 / 9 distinct values in A / P / R) must be value-indexed"
+    monkeypatch.setenv("PAMG_VALUE_INDEX", "0")
+    A, h, c0 = make(dims, pp, None, **FORMATS[fmt])
+    assert not any(c0.stats().value_indexed)
+    for l in range(len(h["levels"]) - 1):
+        lev, nxt = h["levels"][l], h["levels"][l + 1]
+        n, nc = h["global"]["levels"][l]["A"].shape[0], h["global"]["levels"][l + 1]["A"].shape[0]
+        b_, x_, ec = det_vector(n, 41), det_vector(n, 42), det_vector(nc, 43)
+        for a, b in zip(c.spmv(l, own_parts(lev, x_)), c0.spmv(l, own_parts(lev, x_))):
+            assert np.array_equal(a, b)
+        ra, rb = c.residual_restrict(l, own_parts(lev, b_), own_parts(lev, x_)), c0.residual_restrict(l, own_parts(lev, b_), own_parts(lev, x_))
+        for a, b in zip(ra[0] + ra[1], rb[0] + rb[1]):
+            assert np.array_equal(a, b)
+        for a, b in zip(c.prolong_correct(l, own_parts(nxt, ec), own_parts(lev, x_)), c0.prolong_correct(l, own_parts(nxt, ec), own_parts(lev, x_))):
+            assert np.array_equal(a, b)
+        for a, b in zip(c.smooth(l, 2, own_parts(lev, b_), own_parts(lev, x_)), c0.smooth(l, 2, own_parts(lev, b_), own_parts(lev, x_))):
+            assert np.array_equal(a, b)
+    lev = h["levels"][0]
+    rhs = A @ det_vector(A.shape[0], 17)
+    for a, b in zip(c.vcycle(own_parts(lev, rhs)), c0.vcycle(own_parts(lev, rhs))):
+        assert np.array_equal(a, b)
+    (x, it, hist, ok), (x0, it0, hist0, ok0) = c.pcg(own_parts(lev, rhs)), c0.pcg(own_parts(lev, rhs))
+    assert ok and ok0 and it == it0 and np.array_equal(hist, hist0)
+    for a, b in zip(x, x0):
+        assert np.array_equal(a, b)
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, rhs))           # and the oracle, as for every other format
+    assert it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
+
+
+@pytest.mark.parametrize("smoother", ["l1jacobi", "chebyshev"])
+def test_value_indexed_sell_other_smoothers(smoother, monkeypatch):
+    monkeypatch.setenv("PAMG_VALUE_INDEX", "1")
+    oopts = {"smoother": smoother}
+    A, h, c = make((20, 20, 20), (2, 2, 2), oopts, **FORMATS["sell2"])
+    assert c.stats().value_indexed[0] == 7
+    lev = h["levels"][0]
+    b = det_vector(A.shape[0], 5)
+    ref = own_of(lev, O.vcycle(h, O.pvector_from_global(lev, b)))
+    assert rel_err(c.vcycle(own_parts(lev, b)), ref) <= TOL_VCYCLE
+    xs, it_ref, hist_ref = O.pcg(h, O.pvector_from_global(lev, b))
+    x, it, hist, ok = c.pcg(own_parts(lev, b))
+    assert ok and it == it_ref and np.allclose(hist, hist_ref, rtol=1e-7)
