@@ -243,9 +243,16 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     if (which == PAMG_R_OO && getenv("PAMG_R_SIGMA")) forced_sigma = atoi(getenv("PAMG_R_SIGMA"));
     if (forced_sigma > 0) sigma = forced_sigma;
     sell_layout(m, C, sigma, sh, false);
+    // few distinct values (stencil matrices, their prolongators): value-indexed storage, 5 instead of 12 bytes per entry
+    bool vi_ok = false;
+    {
+      const char* e = getenv("PAMG_VALUE_INDEX");
+      vi_ok = rpt == 2 && !(e && atoi(e) == 0) && value_dictionary(m, sh.dict);
+    }
     // auto sigma: sort inside windows only when the unsorted padding is large (the permutation costs more than
-    // ~20 % padding does: P at 256^3 runs 0.228 ms unsorted with 1.16x fill, 0.240 ms sorted with 1.01x)
-    const double sort_fill = getenv("PAMG_SELL_SORT_FILL") ? atof(getenv("PAMG_SELL_SORT_FILL")) : 1.25;
+    // ~20 % padding does: P at 256^3 runs 0.228 ms unsorted with 1.16x fill, 0.240 ms sorted with 1.01x).  A value-indexed
+    // block pads with 5-byte entries and pays the same for the permutation: 0.202 ms unsorted (1.41x) vs 0.229 ms sorted
+    const double sort_fill = getenv("PAMG_SELL_SORT_FILL") ? atof(getenv("PAMG_SELL_SORT_FILL")) : (vi_ok ? 2.0 : 1.25);
     if (o.sell_sigma <= 0 && forced_sigma <= 0 && sh.fill > sort_fill) {
       SellHost s2;
       sell_layout(m, C, 64 * C, s2, false);
@@ -259,14 +266,11 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
       d.sl_col.upload(sh.col);
       d.sl_val.upload(sh.val);
       d.sell_vi = false;
-      {  // few distinct values (stencil matrices, their prolongators): value-indexed storage, 5 instead of 12 bytes per entry
-        const char* e = getenv("PAMG_VALUE_INDEX");
-        if (rpt == 2 && !(e && atoi(e) == 0) && value_dictionary(m, sh.dict)) {
-          sell_value_index(sh);
-          d.sl_vidx.upload(sh.vidx);
-          d.sl_dict.upload(sh.dict);
-          d.sell_vi = true;
-        }
+      if (vi_ok) {
+        sell_value_index(sh);
+        d.sl_vidx.upload(sh.vidx);
+        d.sl_dict.upload(sh.dict);
+        d.sell_vi = true;
       }
       d.sell_perm = sh.permuted;
       if (sh.permuted) d.sl_perm.upload(sh.perm);
@@ -513,7 +517,7 @@ struct Engine::Impl {
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
   int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
-  int vi_variant = 0;       // value-indexed SELL kernel: 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM> (env PAMG_VI_VARIANT)
+  int vi_variant = 0;       // value-indexed SELL kernel: 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM>, 2 = software-pipelined (env PAMG_VI_VARIANT)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
   bool counting = true;
@@ -690,7 +694,7 @@ void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, 
     if (vi && rpt == 2 && !try_unified) {  // value-indexed operator: its own kernel (the experimental variants below do not apply)
       *was_unified = false;
       using KernVi = void (*)(SellViView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
-      KernVi kv = vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2> : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
+      KernVi kv = vi_variant == 2 ? (KernVi)k_spmv_sell_vi_pipe<MD, DT> : vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2> : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
       kv<<<main_grid(L, (const void*)kv), BLOCK, 0, L.s>>>(*vi, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
       return;
     }
@@ -924,7 +928,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   I.have_ipc.assign(I.nparts, 0);
   const pamg_options& o = h->opts;
   if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
-  if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(1, atoi(vv)));
+  if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(2, atoi(vv)));
 
   // global decisions (identical in every process because the metadata is replicated)
   I.need_halo_A.assign(I.L, 0);

@@ -1115,6 +1115,143 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi(SellViView A, cons
   if (DOT) dot_finish(s_acc[threadIdx.x], partials, st, &st->ticket[0], rc, publish, 0, red_slot);
 }
 
+// Software-pipelined form of the value-indexed kernel.  The plain form above is LATENCY bound once the bytes are halved
+// (256^3: 0.221 ms for 0.86 GB, 3.9 TB/s): per slice a warp walks three dependent memory latencies -- extents -> columns /
+// indices -> x gathers -- and 24 resident warps per SM cannot cover them.  Here a warp keeps the NEXT slice's columns and
+// indices in flight (registers) while it gathers, multiplies and stores the CURRENT one, and the extents are loaded two
+// slices ahead: one latency (the gathers) stays on the chain.  The first U = 8 entries of a row are pipelined (all of a
+// 7-point row, all of a prolongator row); longer slices finish in a plain tail loop.  Same products, same order, same bits.
+template <int MODE, bool DOT>
+__global__ void __launch_bounds__(BLOCK, 2) k_spmv_sell_vi_pipe(SellViView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
+                                                              double* partials, RedCtx rc, int publish, int red_slot) {
+  constexpr int U = 8;
+  if (st->done) return;
+  trace_mark(st);
+  const int n_main = (int)gridDim.x - fh.n_pack - fh.n_bnd;
+  const int bid = (int)blockIdx.x - fh.n_pack - (fh.bnd_first ? fh.n_bnd : 0);
+  const int b0 = fh.n_pack + (fh.bnd_first ? 0 : n_main);  // first boundary CTA
+  if ((int)blockIdx.x < fh.n_pack || ((int)blockIdx.x >= b0 && (int)blockIdx.x < b0 + fh.n_bnd)) {  // halo roles
+    double racc = 0.0;
+    if ((int)blockIdx.x < fh.n_pack)
+      pack_role(fh, st, blockIdx.x);
+    else
+      racc = boundary_role<MODE, DOT>(fh, x, a, st, (int)blockIdx.x - b0);
+    if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+    return;
+  }
+  __shared__ double s_dict[256];
+  __shared__ double s_acc[DOT ? BLOCK : 1];
+  s_dict[threadIdx.x] = A.dict[threadIdx.x];  // BLOCK == 256
+  if (DOT) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = BLOCK / 32;
+  const int stride = n_main * wpb;
+  const int2* __restrict__ colb = reinterpret_cast<const int2*>(A.col) + lane;
+  const unsigned short* __restrict__ idxb = reinterpret_cast<const unsigned short*>(A.vidx) + lane;
+  int sl = bid * wpb + (threadIdx.x >> 5);
+  // extents of the current slice and of the next one; columns / indices of the current slice
+  int o0 = 0, w = 0, o0n = 0, wn = 0;
+  if (sl < A.nslices) {
+    o0 = A.slice_off[sl];
+    w = A.slice_off[sl + 1] - o0;
+  }
+  if (sl + stride < A.nslices) {
+    o0n = A.slice_off[sl + stride];
+    wn = A.slice_off[sl + stride + 1] - o0n;
+  }
+  int2 c[U];
+  unsigned short iv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    c[u] = make_int2(0, 0);
+    iv[u] = 0;
+    if (u < w) {
+      c[u] = __ldcs(colb + (size_t)(o0 + u) * 32);
+      iv[u] = __ldcs(idxb + (size_t)(o0 + u) * 32);
+    }
+  }
+  for (; sl < A.nslices; sl += stride) {
+    // ---- stage A: extents two slices ahead, columns / indices and epilogue prefetches of the next slice
+    int o0nn = 0, wnn = 0;
+    if (sl + 2 * stride < A.nslices) {
+      o0nn = A.slice_off[sl + 2 * stride];
+      wnn = A.slice_off[sl + 2 * stride + 1] - o0nn;
+    }
+    int2 cn[U];
+    unsigned short ivn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      cn[u] = make_int2(0, 0);
+      ivn[u] = 0;
+      if (u < wn) {
+        cn[u] = __ldcs(colb + (size_t)(o0n + u) * 32);
+        ivn[u] = __ldcs(idxb + (size_t)(o0n + u) * 32);
+      }
+    }
+    const int slot0 = sl * 64 + lane * 2;
+    int r0 = slot0, r1 = slot0 + 1;
+    if (A.perm) {
+      if (r0 < A.nrows) r0 = A.perm[r0];
+      if (slot0 + 1 < A.nrows) r1 = A.perm[slot0 + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = k ? r1 : r0;
+      if (slot0 + k < A.nrows) {
+        if (fh.skip) asm volatile("prefetch.global.L1 [%0];" ::"l"(fh.skip + r));
+        if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) prefetch_l1(a.in0 + r);
+        if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) prefetch_l1(a.w + r);
+        if (MODE == M_CHEB && a.aux) prefetch_l1(a.aux + r);
+        if (DOT && a.dotv != a.in0) prefetch_l1(a.dotv + r);
+      }
+    }
+    // ---- stage B: the current slice
+    double xv[U][2];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < w) {
+        xv[u][0] = x[c[u].x];
+        xv[u][1] = x[c[u].y];
+      }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < w) {
+        s0 = __dadd_rn(s0, __dmul_rn(s_dict[iv[u] & 0xffu], xv[u][0]));
+        s1 = __dadd_rn(s1, __dmul_rn(s_dict[iv[u] >> 8], xv[u][1]));
+      }
+    for (int j = U; j < w; ++j) {  // rows longer than the pipelined part
+      const int2 cc = __ldcs(colb + (size_t)(o0 + j) * 32);
+      const unsigned short ii = __ldcs(idxb + (size_t)(o0 + j) * 32);
+      s0 = __dadd_rn(s0, __dmul_rn(s_dict[ii & 0xffu], x[cc.x]));
+      s1 = __dadd_rn(s1, __dmul_rn(s_dict[ii >> 8], x[cc.y]));
+    }
+    double contrib = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = k ? r1 : r0;
+      if (slot0 + k < A.nrows) {
+        if (fh.skip && fh.skip[r]) continue;
+        const double res = apply_epilogue<MODE, false>(a, r, k ? s1 : s0);
+        if (DOT) contrib += a.dotv[r] * res;
+      }
+    }
+    if (DOT) s_acc[threadIdx.x] += contrib;
+    // ---- rotate
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      c[u] = cn[u];
+      iv[u] = ivn[u];
+    }
+    o0 = o0n;
+    w = wn;
+    o0n = o0nn;
+    wn = wnn;
+  }
+  if (DOT) dot_finish(s_acc[threadIdx.x], partials, st, &st->ticket[0], rc, publish, 0, red_slot);
+}
+
 // The unified-role kernel (RPT = 2, U = 4).  A kernel of its own: with the role code inlined into k_spmv_sell, ptxas gave
 // three of the production instantiations 80 instead of 72 registers and a worse load schedule (L0 Jacobi +5 %, P0 2.2x).
 template <int MODE, bool DOT>

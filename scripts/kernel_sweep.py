@@ -60,7 +60,9 @@ ENVS = {
     "auto-sort1.1": dict(PAMG_SELL_SORT_FILL="1.1"),
     "auto-novi": dict(PAMG_VALUE_INDEX="0"),       # fp64 values everywhere (round-2 kernels)
     "auto-vi1": dict(PAMG_VI_VARIANT="1"),         # value-indexed kernel <U 8, 2 CTAs/SM>
-    "auto-vi-nosort": dict(PAMG_SELL_SORT_FILL="9"),
+    "auto-vi2": dict(PAMG_VI_VARIANT="2"),         # software-pipelined value-indexed kernel
+    "auto-vi-sorted": dict(PAMG_SELL_SORT_FILL="1.25"),
+    "auto-vi2-sorted": dict(PAMG_VI_VARIANT="2", PAMG_SELL_SORT_FILL="1.25"),
     "auto-pf1": dict(PAMG_SELL_PF="1"),
     "auto-pf3": dict(PAMG_SELL_PF="3"),
     "auto-pf5": dict(PAMG_SELL_PF="5"),
