@@ -192,7 +192,8 @@ int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double
  * as the upload does, so that their invariants can be checked without a GPU.  Output arrays may be NULL; call once
  * with NULL arrays to get the sizes.
  * SELL-C-sigma: slice sl holds rows perm[sl*C .. sl*C+C); entry j of slot q is at (slice_off[sl] + j) * C + q;
- *   stored = slice_off[n_slices] * C entries; padding is (0.0, a valid column).
+ *   stored = slice_off[n_slices] * C entries; padding is (0.0, a valid column).  sigma = -R (rows_per_slice = 32 R) gives the interleaved
+ *   layout of the value-indexed kernel with R rows per lane: position lane * R + k of a full slice holds its row k * 32 + lane.
  * CSR-stream: n_blocks + 1 {first_row, first_entry} pairs (the last one = {nrows, nnz}); n_blocks = -1 when a row
  *   does not fit max_entries.
  * boundary rows: rows that also have own-ghost entries, stored whole (own-column entries [ptr[k], mid[k]), ghost-column

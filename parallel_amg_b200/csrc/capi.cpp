@@ -323,7 +323,8 @@ int pamg_layout_sell(pamg_ctx* c, int32_t level, int32_t part, int32_t which, in
     need(which == PAMG_A_OO || which == PAMG_P_OO || which == PAMG_R_OO, "SELL applies to own-own blocks");
     need(rows_per_slice >= 1 && rows_per_slice <= 1024 && n_slices && stored && permuted, "bad arguments");
     SellHost sh;
-    sell_layout(pl.blk[which], rows_per_slice, sigma, sh, col != nullptr || val != nullptr);
+    const int inter = sigma < 0 ? -sigma : 0;  // sigma = -R: the interleaved layout (R rows per lane, rows_per_slice = 32 R)
+    sell_layout(pl.blk[which], rows_per_slice, inter ? 1 : sigma, sh, col != nullptr || val != nullptr, inter);
     const int64_t ns = (int64_t)sh.off.size() - 1;
     *n_slices = ns;
     *stored = (int64_t)sh.off[ns] * rows_per_slice;
@@ -346,7 +347,8 @@ int pamg_layout_sell_values(pamg_ctx* c, int32_t level, int32_t part, int32_t wh
     SellHost sh;
     const bool ok = value_dictionary(pl.blk[which], sh.dict);
     *indexed = ok ? 1 : 0;
-    sell_layout(pl.blk[which], rows_per_slice, sigma, sh, ok && vidx != nullptr);
+    const int inter = sigma < 0 ? -sigma : 0;
+    sell_layout(pl.blk[which], rows_per_slice, inter ? 1 : sigma, sh, ok && vidx != nullptr, inter);
     *stored = (int64_t)sh.off[sh.off.size() - 1] * rows_per_slice;
     if (!ok) return PAMG_OK;
     if (dict) std::memcpy(dict, sh.dict.data(), 256 * sizeof(double));

@@ -84,6 +84,12 @@ struct DevCsr {
   DBuf<uint8_t> sl_vidx;
   DBuf<double> sl_dict;
   bool sell_vi = false;
+  // the same with four interleaved rows per lane (slices of 128 rows, kernels.cuh k_spmv_sell_vi4): its own slice extents / columns / indices
+  DBuf<int32_t> v4_off, v4_col;
+  DBuf<uint8_t> v4_idx;
+  int nslices4 = 0;
+  bool sell_vi4 = false;
+  SellViView vi4view() const { return SellViView{v4_off.p, v4_col.p, v4_idx.p, sl_dict.p, nullptr, nrows, nslices4}; }
   SellViView viview() const { return SellViView{sl_off.p, sl_col.p, sl_vidx.p, sl_dict.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
   CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
   StreamView sview() const { return StreamView{blk.p, ptr.p, col.p, val.p, nrows, nblocks}; }
@@ -182,6 +188,8 @@ int pick_lanes(double mean) {
 }
 
 // fmt: PAMG_FORMAT_* requested for this block (own-ghost blocks are always compressed-row CSR)
+constexpr int VI_DEFAULT_VARIANT = 0;  // value-indexed kernel when PAMG_VI_VARIANT is not set (Engine::Impl::vi_variant)
+
 void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, int fmt, const pamg_options& o, int which,
                int rpt_override = 0) {
   const int64_t nr = m.nrows;
@@ -192,6 +200,7 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
   d.nblocks = 0;
   d.sell_rpt = 0;
   d.sell_vi = false;
+  d.sell_vi4 = false;
   d.short_rows = false;
   if (!m.ptr.empty()) {
     int64_t mx = 0;
@@ -271,6 +280,18 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
         d.sl_vidx.upload(sh.vidx);
         d.sl_dict.upload(sh.dict);
         d.sell_vi = true;
+        const char* vv = getenv("PAMG_VI_VARIANT");
+        if ((vv ? atoi(vv) : VI_DEFAULT_VARIANT) == 3 && !sh.permuted) {  // four interleaved rows per lane: a second, 128-row slicing
+          SellHost s4;
+          s4.dict = sh.dict;
+          sell_layout(m, 128, 1, s4, true, 4);
+          sell_value_index(s4);
+          d.v4_off.upload(s4.off);
+          d.v4_col.upload(s4.col);
+          d.v4_idx.upload(s4.vidx);
+          d.nslices4 = (int)s4.off.size() - 1;
+          d.sell_vi4 = true;
+        }
       }
       d.sell_perm = sh.permuted;
       if (sh.permuted) d.sl_perm.upload(sh.perm);
@@ -517,7 +538,7 @@ struct Engine::Impl {
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
   int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
-  int vi_variant = 0;       // value-indexed SELL kernel: 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM>, 2 = software-pipelined (env PAMG_VI_VARIANT)
+  int vi_variant = VI_DEFAULT_VARIANT;  // value-indexed SELL kernel (3 = four interleaved rows per lane): 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM>, 2 = software-pipelined (env PAMG_VI_VARIANT)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
   bool counting = true;
@@ -694,7 +715,7 @@ void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, 
     if (vi && rpt == 2 && !try_unified) {  // value-indexed operator: its own kernel (the experimental variants below do not apply)
       *was_unified = false;
       using KernVi = void (*)(SellViView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
-      KernVi kv = vi_variant == 2 ? (KernVi)k_spmv_sell_vi_pipe<MD, DT> : vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2> : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
+      KernVi kv = vi_variant == 3 ? (KernVi)k_spmv_sell_vi4<MD, DT> : vi_variant == 2 ? (KernVi)k_spmv_sell_vi_pipe<MD, DT> : vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2> : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
       kv<<<main_grid(L, (const void*)kv), BLOCK, 0, L.s>>>(*vi, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
       return;
     }
@@ -840,10 +861,12 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     L.grid = std::max(n_main, 1);
     bool was_unified = false;
     SellViView viv{};
-    if (m.sell_vi) viv = m.viview();
+    const bool use_vi4 = m.sell_vi4 && I.vi_variant == 3 && !try_unified;
+    if (m.sell_vi) viv = use_vi4 ? m.vi4view() : m.viview();
+    if (use_vi4) L.grid = std::max((m.nslices4 + BLOCK / 32 - 1) / (BLOCK / 32), 1);
     if (m.sell_rpt)
       launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
-                  try_unified, I.unified_mode, &was_unified, m.sell_vi ? &viv : nullptr, I.vi_variant);
+                  try_unified, I.unified_mode, &was_unified, m.sell_vi ? &viv : nullptr, use_vi4 ? 3 : std::min(I.vi_variant, 2));
     else if (m.stream)
       launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
@@ -928,7 +951,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   I.have_ipc.assign(I.nparts, 0);
   const pamg_options& o = h->opts;
   if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
-  if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(2, atoi(vv)));
+  if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(3, atoi(vv)));
 
   // global decisions (identical in every process because the metadata is replicated)
   I.need_halo_A.assign(I.L, 0);

@@ -100,12 +100,22 @@ inline void sell_value_index(SellHost& sh, int n_distinct_hint = 256) {
   }
 }
 
-inline void sell_layout(const LocalCsr& m, int C, int sigma, SellHost& out, bool fill_arrays) {
+// interleave = R > 0 (C = 32 R, no sorting): inside every FULL slice position lane * R + k holds row k * 32 + lane of the slice, so
+// that a lane's R rows lie 32 apart and the 32 lanes of a warp touch 32 CONSECUTIVE rows at a time (coalesced gathers and
+// epilogue accesses); the kernel computes that map arithmetically, `perm` is filled for the host-side checks only.  The last,
+// partial slice keeps the identity.
+inline void sell_layout(const LocalCsr& m, int C, int sigma, SellHost& out, bool fill_arrays, int interleave = 0) {
   const int64_t nr = m.nrows;
   const int64_t ns = (nr + C - 1) / C;
   out.perm.resize(nr);
   for (int64_t i = 0; i < nr; ++i) out.perm[i] = (int32_t)i;
   out.permuted = false;
+  if (interleave > 0) {
+    if (C != 32 * interleave || sigma > 1) throw std::runtime_error("interleaved SELL layout: C = 32 R and no sorting");
+    for (int64_t sl = 0; (sl + 1) * C <= nr; ++sl)
+      for (int lane = 0; lane < 32; ++lane)
+        for (int k = 0; k < interleave; ++k) out.perm[sl * C + lane * interleave + k] = (int32_t)(sl * C + k * 32 + lane);
+  }
   if (sigma > 1) {
     for (int64_t w0 = 0; w0 < nr; w0 += sigma) {
       const int64_t w1 = std::min<int64_t>(nr, w0 + sigma);

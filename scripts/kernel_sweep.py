@@ -61,6 +61,7 @@ ENVS = {
     "auto-novi": dict(PAMG_VALUE_INDEX="0"),       # fp64 values everywhere (round-2 kernels)
     "auto-vi1": dict(PAMG_VI_VARIANT="1"),         # value-indexed kernel <U 8, 2 CTAs/SM>
     "auto-vi2": dict(PAMG_VI_VARIANT="2"),         # software-pipelined value-indexed kernel
+    "auto-vi3": dict(PAMG_VI_VARIANT="3"),         # four interleaved rows per lane
     "auto-vi-sorted": dict(PAMG_SELL_SORT_FILL="1.25"),
     "auto-vi2-sorted": dict(PAMG_VI_VARIANT="2", PAMG_SELL_SORT_FILL="1.25"),
     "auto-pf1": dict(PAMG_SELL_PF="1"),

@@ -33,7 +33,7 @@ def csr_of(c, l, p, which):
     return sp.csr_matrix((d, ix, ip), shape=(len(ip) - 1, max(ncols, 1)))
 
 
-@pytest.mark.parametrize("C,sigma", [(32, 1), (64, 1), (64, 256), (32, 96)])
+@pytest.mark.parametrize("C,sigma", [(32, 1), (64, 1), (64, 256), (32, 96), (128, -4)])
 def test_sell_layout_invariants(ctx, C, sigma):
     for l, p, which in blocks(ctx):
         A = csr_of(ctx, l, p, which)
@@ -42,7 +42,13 @@ def test_sell_layout_invariants(ctx, C, sigma):
         off, col, val, perm = lay["slice_off"], lay["col"], lay["val"], lay["perm"]
         lens = np.diff(A.indptr)
         assert sorted(perm.tolist()) == list(range(nr))                       # a permutation
-        if sigma <= 1:
+        if sigma < 0:                                                          # interleaved: lane * R + k  <->  row k * 32 + lane
+            R = -sigma
+            full = (nr // C) * C
+            q = np.arange(full)
+            assert np.array_equal(perm[:full], (q // C) * C + (q % R) * 32 + (q % C) // R)
+            assert np.array_equal(perm[full:], np.arange(full, nr))
+        elif sigma <= 1:
             assert not lay["permuted"] and np.array_equal(perm, np.arange(nr))
         else:
             for w0 in range(0, nr, sigma):                                     # inside its window, longest rows first
@@ -114,7 +120,7 @@ def test_boundary_rows_are_the_rows_with_ghost_columns(ctx):
             assert np.array_equal(lay["val"][m:b], d[ip[r]:ip[r + 1]])
 
 
-@pytest.mark.parametrize("C,sigma", [(64, 1), (64, 256)])
+@pytest.mark.parametrize("C,sigma", [(64, 1), (64, 256), (128, -4)])
 def test_value_indexed_sell_storage(ctx, C, sigma):
     """kernels.cuh k_spmv_sell_vi reads dict[vidx[k]] instead of val[k]: the dictionary must reproduce every stored value BIT FOR BIT
     (padding -> entry 0 = +0.0), hold <= 255 distinct non-zero patterns in ascending pattern order, and blocks with more distinct values

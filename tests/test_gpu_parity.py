@@ -455,7 +455,7 @@ def test_fgmres_nonsymmetric_operator():
 # ---- value-indexed SELL storage (kernels.cuh k_spmv_sell_vi) ---------------------------------------------------------------------
 @pytest.mark.parametrize("dims,pp", [((28, 28, 28), (1, 1, 1)), ((33, 31, 17), (3, 2, 1)), ((200, 200), (2, 2))])
 @pytest.mark.parametrize("fmt", ["sell2", "sell2-sorted"])
-@pytest.mark.parametrize("variant", ["0", "1", "2"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3"])
 def test_value_indexed_sell_is_bit_identical_to_fp64_values(dims, pp, fmt, variant, monkeypatch):
     """An operator with <= 255 distinct values is stored as columns + one byte per entry; every kernel mode must give the SAME BITS as
     the fp64-valued SELL kernels (same products, same order): all level operators, smoothers, the cycle, the PCG history."""
