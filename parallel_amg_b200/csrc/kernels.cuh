@@ -1313,15 +1313,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
           c[u] = __ldcs(cj + u * 32);
           iv[u] = __ldcs(ij + u * 32);
         }
+      // The gathers must not drift up between the column loads: ptxas interleaved them in four of the six modes (column load,
+      // its four gathers, next column load, ...: one exposed latency per entry instead of one per step), and neither a
+      // compiler barrier nor a warp barrier holds non-coherent loads back.  A data dependence does: the gather base is offset by
+      // the sign of the OR of all the step's columns -- zero, since columns are non-negative, but not provably so.
+      int allc = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u < w) allc |= c[u].x | c[u].y | c[u].z | c[u].w | (int)(iv[u] >> 1);  // the index loads too: they go out with the columns
+      const int z = allc >> 31;
       double xv[U][4];
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (j0 + u < w) {
-          xv[u][0] = x[c[u].x];
-          xv[u][1] = x[c[u].y];
-          xv[u][2] = x[c[u].z];
-          xv[u][3] = x[c[u].w];
+          xv[u][0] = x[c[u].x + z];
+          xv[u][1] = x[c[u].y + z];
+          xv[u][2] = x[c[u].z + z];
+          xv[u][3] = x[c[u].w + z];
         }
+      asm volatile("" ::: "memory");
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (j0 + u < w) {
@@ -1329,14 +1339,36 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
           for (int k = 0; k < 4; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(s_dict[(iv[u] >> (8 * k)) & 0xffu], xv[u][k]));
         }
     }
+    // epilogue, two rows at a time: their operand loads first (L1 hits, requested before the entry loop), then arithmetic and stores
     double contrib = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = r_first + k * rstep;
-      if (r < A.nrows) {
-        if (fh.skip && fh.skip[r]) continue;
-        const double res = apply_epilogue<MODE, false>(a, r, s[k]);
-        if (DOT) contrib += a.dotv[r] * res;
+    for (int h = 0; h < 4; h += 2) {
+      bool live[2];
+      double e_in0[2], e_in1[2], e_w[2], e_aux[2], e_dot[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = r_first + (h + k) * rstep;
+        live[k] = r < A.nrows && !(fh.skip && fh.skip[r]);
+        e_in0[k] = e_in1[k] = e_w[k] = e_aux[k] = e_dot[k] = 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = r_first + (h + k) * rstep;
+        if (live[k]) {
+          if (MODE == M_RESID || MODE == M_JACOBI || MODE == M_ADD || MODE == M_CHEB) e_in0[k] = a.in0[r];
+          if (MODE == M_JACOBI || MODE == M_CHEB) e_in1[k] = a.in1[r];
+          if (MODE == M_JACOBI || MODE == M_CHEB || (MODE == M_RESTRICT && a.out2)) e_w[k] = a.w[r];
+          if (MODE == M_CHEB && a.aux) e_aux[k] = a.aux[r];
+          if (DOT) e_dot[k] = (a.dotv == a.in0 && (MODE == M_JACOBI || MODE == M_RESID)) ? e_in0[k] : a.dotv[r];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = r_first + (h + k) * rstep;
+        if (live[k]) {
+          const double res = stream_epilogue<MODE>(a, r, s[h + k], e_in0[k], e_in1[k], e_w[k], e_aux[k]);
+          if (DOT) contrib += e_dot[k] * res;
+        }
       }
     }
     if (DOT) s_acc[threadIdx.x] += contrib;
