@@ -390,13 +390,22 @@ def measure(workload, args, rank, world, local_rank, steps, warmup, headline):
     kern = {}
     info = c.level_info(0, mine[0])
     n_own, nnz_oo = info.n_own, info.nnz[0]
-    spmv_bytes = 12 * nnz_oo + 4 * (n_own + 1) + 8 * n_own + 8 * n_own
-    algo = {0: ("spmv A0", spmv_bytes), 1: ("jacobi sweep A0", spmv_bytes + 16 * n_own)}
-    for kind, (name, nbytes) in algo.items():
-        ms = c.time_kernel(kind, 0, 13, True)[3:]
-        kern[name] = dict(ms=float(np.mean(ms)), gbs=nbytes / (float(np.mean(ms)) * 1e-3) / 1e9, bytes=int(nbytes))
     stt = c.stats()
-    kname = {L.FORMAT_SELL: "k_spmv_sell<RPT=2,MUL> (SELL-C-sigma, C=64, 128-bit value loads, persistent CTAs)",
+    # SURVEY 8(d) bytes of a CSR SpMV with fp64 values (12 B per entry + row pointers + x + y) ...
+    csr_bytes = 12 * nnz_oo + 4 * (n_own + 1) + 8 * n_own + 8 * n_own
+    # ... and what the kernel that runs has to move: a value-indexed SELL block (<= 255 distinct values -> int32 column +
+    # one byte per entry, no row pointers) moves 5 B per entry.  The roofline fraction is taken on the bytes of the format that runs;
+    # the fp64-CSR-equivalent rate is reported beside it.
+    vi_a0 = bool(stt.value_indexed[0] & 1)
+    spmv_bytes = (5 * nnz_oo + 16 * n_own) if vi_a0 else csr_bytes
+    algo = {0: ("spmv A0", spmv_bytes, csr_bytes), 1: ("jacobi sweep A0", spmv_bytes + 16 * n_own, csr_bytes + 16 * n_own)}
+    for kind, (name, nbytes, eq) in algo.items():
+        ms = c.time_kernel(kind, 0, 13, True)[3:]
+        kern[name] = dict(ms=float(np.mean(ms)), gbs=nbytes / (float(np.mean(ms)) * 1e-3) / 1e9, bytes=int(nbytes),
+                          fp64_csr_equivalent_gbs=eq / (float(np.mean(ms)) * 1e-3) / 1e9, fp64_csr_equivalent_bytes=int(eq))
+    kname = {L.FORMAT_SELL: ("k_spmv_sell_vi4<MUL> (value-indexed SELL-C-sigma: int32 column + 1 byte into a dictionary of the distinct fp64 "
+                             "values, C=128, 128-bit column loads, 4 interleaved rows per lane, persistent CTAs)") if vi_a0 else
+             "k_spmv_sell<RPT=2,MUL> (SELL-C-sigma, C=64, 128-bit value loads, persistent CTAs)",
              L.FORMAT_STREAM: "k_spmv_stream<MUL> (CSR-stream, 128-bit coalesced loads, smem-staged products)"}.get(
                  stt.format[0], f"k_spmv<lanes={stt.lanes[0]},MUL> (sub-warp CSR)")
 
@@ -440,10 +449,13 @@ def measure(workload, args, rank, world, local_rank, steps, warmup, headline):
             rec = dict(
                 value=n * steps / (dev_ms * 1e-3), ms_per_step=dev_ms / steps, n=int(n), iters=int(it), levels=c.num_levels(),
                 vcycle_ms=float(np.mean(vc)), wall_ms_per_step=wall_ms / steps, true_residual_rel=true_rel, solution_max_err=sol_err,
-                roofline=dict(bound="hbm", kernel=kname + " level 0: y = A x, fp64 values / int32 columns", achieved=dom["gbs"],
+                roofline=dict(bound="hbm", kernel=kname + " level 0: y = A x, fp64 arithmetic / int32 columns", achieved=dom["gbs"],
                               peak=peak, unit="GB/s", frac=dom["gbs"] / peak, peak_source=peak_src, traffic=ncu_traffic(workload, args.gpus),
                               algorithmic_bytes_per_launch=dom["bytes"], ms_per_launch=dom["ms"],
-                              frac_of_nominal_8TBs=dom["gbs"] / 8000.0),
+                              frac_of_nominal_8TBs=dom["gbs"] / 8000.0, value_indexed=vi_a0,
+                              fp64_csr_equivalent=dict(bytes_per_launch=dom["fp64_csr_equivalent_bytes"], gbs=dom["fp64_csr_equivalent_gbs"],
+                                                       frac=dom["fp64_csr_equivalent_gbs"] / peak,
+                                                       note="SURVEY 8(d) bytes of the same product with 12 B per entry; > 1 means fewer bytes cross the pins than a CSR fp64 kernel needs")),
                 kernels=kern,
                 e2e=dict(value=n * steps / (e2e_ms * 1e-3), unit="DOF/s", h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
                          ms_per_step=e2e_ms / steps),

@@ -353,7 +353,7 @@ int pamg_layout_sell_values(pamg_ctx* c, int32_t level, int32_t part, int32_t wh
     if (!ok) return PAMG_OK;
     if (dict) std::memcpy(dict, sh.dict.data(), 256 * sizeof(double));
     if (vidx) {
-      sell_value_index(sh);
+      sell_value_index(sh, 1);
       std::memcpy(vidx, sh.vidx.data(), (size_t)*stored);
     }
     return PAMG_OK;

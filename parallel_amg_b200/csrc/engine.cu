@@ -18,6 +18,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "engine.hpp"
@@ -89,8 +90,10 @@ struct DevCsr {
   DBuf<uint8_t> v4_idx;
   int nslices4 = 0;
   bool sell_vi4 = false;
-  SellViView vi4view() const { return SellViView{v4_off.p, v4_col.p, v4_idx.p, sl_dict.p, nullptr, nrows, nslices4}; }
-  SellViView viview() const { return SellViView{sl_off.p, sl_col.p, sl_vidx.p, sl_dict.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
+  int vi4_ib = 1;   // bytes per index of the 128-row layout: 1 (<= 255 distinct values) or 2 (wide: <= VI_WIDE_MAX - 1)
+  int ndict = 256;  // dictionary entries uploaded
+  SellViView vi4view() const { return SellViView{v4_off.p, v4_col.p, v4_idx.p, sl_dict.p, nullptr, nrows, nslices4, ndict}; }
+  SellViView viview() const { return SellViView{sl_off.p, sl_col.p, sl_vidx.p, sl_dict.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices, 256}; }
   CsrView view() const { return CsrView{ptr.p, col.p, val.p, listed ? rows.p : nullptr, nrows}; }
   StreamView sview() const { return StreamView{blk.p, ptr.p, col.p, val.p, nrows, nblocks}; }
   SellView slview() const { return SellView{sl_off.p, sl_col.p, sl_val.p, sell_perm ? sl_perm.p : nullptr, nrows, nslices}; }
@@ -188,7 +191,9 @@ int pick_lanes(double mean) {
 }
 
 // fmt: PAMG_FORMAT_* requested for this block (own-ghost blocks are always compressed-row CSR)
-constexpr int VI_DEFAULT_VARIANT = 0;  // value-indexed kernel when PAMG_VI_VARIANT is not set (Engine::Impl::vi_variant)
+// value-indexed kernel when PAMG_VI_VARIANT is not set (Engine::Impl::vi_variant): 3 = four interleaved rows per lane (256^3 solve
+// 34.5 ms; 0 = two rows per lane 39.4 ms; fp64 values 43.1 ms; 1 = <U 8, 2 CTAs/SM> and 2 = software-pipelined: slower than 0)
+constexpr int VI_DEFAULT_VARIANT = 3;
 
 void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, int fmt, const pamg_options& o, int which,
                int rpt_override = 0) {
@@ -252,16 +257,21 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
     if (which == PAMG_R_OO && getenv("PAMG_R_SIGMA")) forced_sigma = atoi(getenv("PAMG_R_SIGMA"));
     if (forced_sigma > 0) sigma = forced_sigma;
     sell_layout(m, C, sigma, sh, false);
-    // few distinct values (stencil matrices, their prolongators): value-indexed storage, 5 instead of 12 bytes per entry
-    bool vi_ok = false;
+    // few distinct values (stencil matrices, their prolongators): value-indexed storage, 5 instead of 12 bytes per entry; up to
+    // VI_WIDE_MAX - 1 distinct values (Galerkin matrix of the first coarse level): two index bytes, 6 instead of 12 (128-row layout only)
+    bool vi_ok = false, vi_wide = false;
     {
       const char* e = getenv("PAMG_VALUE_INDEX");
-      vi_ok = rpt == 2 && !(e && atoi(e) == 0) && value_dictionary(m, sh.dict);
+      const char* vv = getenv("PAMG_VI_VARIANT");
+      const bool on = rpt == 2 && !(e && atoi(e) == 0);
+      vi_ok = on && value_dictionary(m, sh.dict, 255);
+      if (on && !vi_ok && (vv ? atoi(vv) : VI_DEFAULT_VARIANT) == 3 && !(e && atoi(e) == 1) && o.sell_sigma <= 1 && forced_sigma <= 0)
+        vi_wide = value_dictionary(m, sh.dict, VI_WIDE_MAX - 1);  // PAMG_VALUE_INDEX=1: one-byte indices only
     }
     // auto sigma: sort inside windows only when the unsorted padding is large (the permutation costs more than
     // ~20 % padding does: P at 256^3 runs 0.228 ms unsorted with 1.16x fill, 0.240 ms sorted with 1.01x).  A value-indexed
     // block pads with 5-byte entries and pays the same for the permutation: 0.202 ms unsorted (1.41x) vs 0.229 ms sorted
-    const double sort_fill = getenv("PAMG_SELL_SORT_FILL") ? atof(getenv("PAMG_SELL_SORT_FILL")) : (vi_ok ? 2.0 : 1.25);
+    const double sort_fill = getenv("PAMG_SELL_SORT_FILL") ? atof(getenv("PAMG_SELL_SORT_FILL")) : ((vi_ok || vi_wide) ? 2.0 : 1.25);
     if (o.sell_sigma <= 0 && forced_sigma <= 0 && sh.fill > sort_fill) {
       SellHost s2;
       sell_layout(m, C, 64 * C, s2, false);
@@ -275,17 +285,22 @@ void build_csr(const LocalCsr& m, bool compress, DevCsr& d, int lanes_override, 
       d.sl_col.upload(sh.col);
       d.sl_val.upload(sh.val);
       d.sell_vi = false;
+      d.sell_vi4 = false;
       if (vi_ok) {
-        sell_value_index(sh);
+        sell_value_index(sh, 1);
         d.sl_vidx.upload(sh.vidx);
-        d.sl_dict.upload(sh.dict);
         d.sell_vi = true;
+      }
+      if (vi_ok || vi_wide) {
+        d.ndict = (int)sh.dict.size();
+        d.sl_dict.upload(sh.dict);
         const char* vv = getenv("PAMG_VI_VARIANT");
         if ((vv ? atoi(vv) : VI_DEFAULT_VARIANT) == 3 && !sh.permuted) {  // four interleaved rows per lane: a second, 128-row slicing
           SellHost s4;
           s4.dict = sh.dict;
           sell_layout(m, 128, 1, s4, true, 4);
-          sell_value_index(s4);
+          d.vi4_ib = vi_ok ? 1 : 2;
+          sell_value_index(s4, d.vi4_ib);
           d.v4_off.upload(s4.off);
           d.v4_col.upload(s4.col);
           d.v4_idx.upload(s4.vidx);
@@ -603,15 +618,15 @@ namespace {
 
 // CTAs of `kernel` that are resident at once on the current device (148 SMs x occupancy): the grid of a
 // kernel with a fused reduction, so that it runs as exactly one wave of persistent CTAs
-int resident_ctas(const void* kernel) {
-  static std::map<std::pair<int, const void*>, int> cache;
+int resident_ctas(const void* kernel, size_t dyn_smem = 0) {
+  static std::map<std::tuple<int, const void*, size_t>, int> cache;
   int dev = 0;
   cudaGetDevice(&dev);
-  auto key = std::make_pair(dev, kernel);
+  auto key = std::make_tuple(dev, kernel, dyn_smem);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, 0) != cudaSuccess) per_sm = 2;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, dyn_smem) != cudaSuccess) per_sm = 2;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   const int r = std::max(1, per_sm * sms);
   cache[key] = r;
@@ -631,9 +646,9 @@ struct LaunchArgs {  // what every SpMV-family launch shares
   int publish, slot;   // fused dot: publish = 1 total goes to every part, 0 a boundary launch completes it
 };
 
-int main_grid(const LaunchArgs& L, const void* kernel) {
+int main_grid(const LaunchArgs& L, const void* kernel, size_t dyn_smem = 0) {
   int n_main = L.grid;
-  if (L.bounded) n_main = std::min(n_main, std::min(resident_ctas(kernel), RED_GRID));
+  if (L.bounded) n_main = std::min(n_main, std::min(resident_ctas(kernel, dyn_smem), RED_GRID));
   return L.fh.n_pack + std::max(n_main, 1) + L.fh.n_bnd;
 }
 
@@ -715,8 +730,13 @@ void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, 
     if (vi && rpt == 2 && !try_unified) {  // value-indexed operator: its own kernel (the experimental variants below do not apply)
       *was_unified = false;
       using KernVi = void (*)(SellViView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
-      KernVi kv = vi_variant == 3 ? (KernVi)k_spmv_sell_vi4<MD, DT> : vi_variant == 2 ? (KernVi)k_spmv_sell_vi_pipe<MD, DT> : vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2> : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
-      kv<<<main_grid(L, (const void*)kv), BLOCK, 0, L.s>>>(*vi, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
+      KernVi kv = vi_variant == 4   ? (KernVi)k_spmv_sell_vi4<MD, DT, 2>
+                  : vi_variant == 3 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1>
+                  : vi_variant == 2 ? (KernVi)k_spmv_sell_vi_pipe<MD, DT>
+                  : vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2>
+                                    : (KernVi)k_spmv_sell_vi<MD, DT, 4, 3>;
+      const size_t dyn = vi_variant >= 3 ? (size_t)vi->ndict * sizeof(double) : 0;  // the 128-row kernel keeps its dictionary in dynamic shared memory
+      kv<<<main_grid(L, (const void*)kv, dyn), BLOCK, dyn, L.s>>>(*vi, L.x, L.a, L.st, L.fh, L.partials, L.rc, L.publish, L.slot);
       return;
     }
     using Kern = void (*)(SellView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
@@ -862,11 +882,12 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     bool was_unified = false;
     SellViView viv{};
     const bool use_vi4 = m.sell_vi4 && I.vi_variant == 3 && !try_unified;
-    if (m.sell_vi) viv = use_vi4 ? m.vi4view() : m.viview();
+    if (m.sell_vi || use_vi4) viv = use_vi4 ? m.vi4view() : m.viview();
     if (use_vi4) L.grid = std::max((m.nslices4 + BLOCK / 32 - 1) / (BLOCK / 32), 1);
     if (m.sell_rpt)
       launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
-                  try_unified, I.unified_mode, &was_unified, m.sell_vi ? &viv : nullptr, use_vi4 ? 3 : std::min(I.vi_variant, 2));
+                  try_unified, I.unified_mode, &was_unified, (m.sell_vi || use_vi4) ? &viv : nullptr,
+                  use_vi4 ? (m.vi4_ib == 2 ? 4 : 3) : (I.vi_variant == 3 ? 0 : I.vi_variant));  // blocks without the 128-row layout (sorted rows): two rows per lane
     else if (m.stream)
       launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
@@ -874,7 +895,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     if (I.naming) {
       static const char* MODES[] = {"mul", "resid", "jacobi", "add", "restrict", "cheb"};
       static const char* OPS[] = {"A", "P", "R"};
-      I.names.push_back(std::string(m.sell_rpt ? (m.sell_vi && !was_unified ? "sell-vi " : "sell ") : m.stream ? "stream " : "csr ") + MODES[op.mode] + (op.dot ? "+dot " : " ") +
+      I.names.push_back(std::string(m.sell_rpt ? ((m.sell_vi || use_vi4) && !was_unified ? (use_vi4 && m.vi4_ib == 2 ? "sell-vi16 " : "sell-vi ") : "sell ") : m.stream ? "stream " : "csr ") + MODES[op.mode] + (op.dot ? "+dot " : " ") +
                         OPS[wsel] + std::to_string(l) + (I.tail_mode ? " tail" : "") + (fh.n_pack ? " +pack" : "") +
                         (fh.n_bnd ? " +bnd" : "") + (was_unified ? " uni" : ""));
       I.naming = false;
@@ -2694,7 +2715,10 @@ void Engine::get_stats(pamg_stats* s) {
     s->value_indexed[l] = 0;
     if (have) {
       const LevelDev& ld = *I.P(0).lev[l];
-      s->value_indexed[l] = (ld.blk[PAMG_A_OO].sell_vi ? 1 : 0) | (ld.blk[PAMG_P_OO].sell_vi ? 2 : 0) | (ld.blk[PAMG_R_OO].sell_vi ? 4 : 0);
+      auto vi_of = [](const DevCsr& m) { return m.sell_vi || m.sell_vi4; };
+      auto wide_of = [](const DevCsr& m) { return m.sell_vi4 && m.vi4_ib == 2; };
+      s->value_indexed[l] = (vi_of(ld.blk[PAMG_A_OO]) ? 1 : 0) | (vi_of(ld.blk[PAMG_P_OO]) ? 2 : 0) | (vi_of(ld.blk[PAMG_R_OO]) ? 4 : 0) |
+                            (wide_of(ld.blk[PAMG_A_OO]) ? 8 : 0) | (wide_of(ld.blk[PAMG_P_OO]) ? 16 : 0) | (wide_of(ld.blk[PAMG_R_OO]) ? 32 : 0);
     }
   }
 }

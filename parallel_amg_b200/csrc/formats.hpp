@@ -32,7 +32,7 @@ struct SellHost {
 
 // Distinct values of m by BIT PATTERN (-0.0 and +0.0 are different entries: the products keep their sign), ascending by
 // pattern behind dict[0] = +0.0.  Returns false as soon as more than 255 are seen (then `dict` is empty).
-inline bool value_dictionary(const LocalCsr& m, std::vector<double>& dict) {
+inline bool value_dictionary(const LocalCsr& m, std::vector<double>& dict, int max_distinct = 255) {
   dict.clear();
   const int64_t nnz = m.nnz();
   auto bits = [](double v) {
@@ -57,7 +57,7 @@ inline bool value_dictionary(const LocalCsr& m, std::vector<double>& dict) {
       auto it = std::lower_bound(mine.begin(), mine.end(), b);
       if (it == mine.end() || *it != b) {
         mine.insert(it, b);
-        if (mine.size() > 255) {
+        if ((int)mine.size() > max_distinct) {
 #pragma omp atomic write
           too_many = true;
         }
@@ -70,33 +70,40 @@ inline bool value_dictionary(const LocalCsr& m, std::vector<double>& dict) {
   std::sort(all.begin(), all.end());
   all.erase(std::unique(all.begin(), all.end()), all.end());
   all.erase(std::remove(all.begin(), all.end(), (uint64_t)0), all.end());  // +0.0 is dict[0] anyway
-  if (all.size() > 255) return false;
-  dict.assign(256, 0.0);
+  if ((int)all.size() > max_distinct) return false;
+  dict.assign(max_distinct <= 255 ? 256 : all.size() + 1, 0.0);  // one-byte form: always 256 entries (unused ones 0.0)
   for (size_t i = 0; i < all.size(); ++i) std::memcpy(&dict[i + 1], &all[i], sizeof(double));
   return true;
 }
 
-// vidx of an already filled SELL layout; dict from value_dictionary (sorted by bit pattern behind dict[0])
-inline void sell_value_index(SellHost& sh, int n_distinct_hint = 256) {
-  (void)n_distinct_hint;
-  std::vector<uint64_t> key(256, 0);
+// vidx of an already filled SELL layout; dict from value_dictionary (sorted by bit pattern behind dict[0]).  index_bytes = 1: one byte
+// per stored entry; 2: two bytes (little endian), for dictionaries beyond 256 entries.
+inline void sell_value_index(SellHost& sh, int index_bytes = 1) {
+  std::vector<uint64_t> key(sh.dict.size(), 0);
   int nd = 1;
-  for (int i = 1; i < 256; ++i) {
+  for (int i = 1; i < (int)sh.dict.size(); ++i) {
     uint64_t b;
     std::memcpy(&b, &sh.dict[i], sizeof(b));
     if (b == 0) break;  // unused tail (a stored +0.0 maps to entry 0)
     key[i] = b;
     nd = i + 1;
   }
+  if (index_bytes == 1 && nd > 256) throw std::runtime_error("value dictionary too large for one-byte indices");
   const int64_t stored = (int64_t)sh.val.size();
-  sh.vidx.assign(sh.val.size(), 0);
+  sh.vidx.assign(sh.val.size() * (size_t)index_bytes, 0);
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < stored; ++k) {
     uint64_t b;
     std::memcpy(&b, &sh.val[k], sizeof(b));
     if (b == 0) continue;
     const auto it = std::lower_bound(key.begin() + 1, key.begin() + nd, b);
-    sh.vidx[k] = (uint8_t)(it - key.begin());
+    const uint32_t ix = (uint32_t)(it - key.begin());
+    if (index_bytes == 1) {
+      sh.vidx[k] = (uint8_t)ix;
+    } else {
+      sh.vidx[2 * k] = (uint8_t)(ix & 0xffu);
+      sh.vidx[2 * k + 1] = (uint8_t)(ix >> 8);
+    }
   }
 }
 

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 namespace pamg {
 
@@ -1027,11 +1028,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell(SellView A, const dou
 struct SellViView {
   const int32_t* slice_off;
   const int32_t* col;
-  const uint8_t* vidx;   // [slice_off[nslices] * 64] dictionary index per stored entry (padding -> the entry holding 0.0)
-  const double* dict;    // [256]
+  const uint8_t* vidx;   // [slice_off[nslices] * C] dictionary index per stored entry (padding -> the entry holding 0.0); one byte each,
+                         // two (little endian) in the wide form of k_spmv_sell_vi4
+  const double* dict;    // [256], wide form: [ndict]
   const int32_t* perm;
   int32_t nrows, nslices;
+  int32_t ndict;         // dictionary entries (wide form: <= VI_WIDE_MAX, copied to dynamic shared memory)
 };
+constexpr int VI_WIDE_MAX = 4096;  // 32 KB of shared memory per CTA
 
 template <int MODE, bool DOT, int U = 4, int MINB = 3>
 __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi(SellViView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
@@ -1258,7 +1262,13 @@ __global__ void __launch_bounds__(BLOCK, 2) k_spmv_sell_vi_pipe(SellViView A, co
 // flight.  Here a warp carries twice the rows through the same number of dependent phases (one 128-bit column load and one
 // 32-bit index load per entry and lane), and because the lanes of a warp now touch 32 CONSECUTIVE rows per access the x
 // gathers and the epilogue cost half the L1 wavefronts per row.  Same products, same order, same bits.
-template <int MODE, bool DOT, int U = 4, int MINB = 3>
+// index of row k (0..3) of a lane in the loaded index word(s); vi_bits: any function of ALL their bits (load-order dependence)
+__device__ __forceinline__ unsigned vi_index(unsigned v, int k) { return (v >> (8 * k)) & 0xffu; }
+__device__ __forceinline__ unsigned vi_index(const uint2& v, int k) { return ((k < 2 ? v.x : v.y) >> (16 * (k & 1))) & 0xffffu; }
+__device__ __forceinline__ unsigned vi_bits(unsigned v) { return v; }
+__device__ __forceinline__ unsigned vi_bits(const uint2& v) { return v.x | v.y; }
+
+template <int MODE, bool DOT, int IB = 1, int U = 4, int MINB = 3>
 __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
                                                             double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
@@ -1275,9 +1285,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
     if (DOT) dot_finish(racc, partials, st, &st->ticket[0], rc, publish, 0, red_slot);
     return;
   }
-  __shared__ double s_dict[256];
+  // IB = 1: one index byte per entry, 256 dictionary entries; IB = 2 (wide): two bytes, up to VI_WIDE_MAX entries (the Galerkin
+  // matrix of level 1 of the Poisson hierarchy has a few hundred to a few thousand distinct values: 6 instead of 12 bytes per entry)
+  extern __shared__ double s_dict[];
   __shared__ double s_acc[DOT ? BLOCK : 1];
-  s_dict[threadIdx.x] = A.dict[threadIdx.x];  // BLOCK == 256
+  for (int i = threadIdx.x; i < A.ndict; i += BLOCK) s_dict[i] = A.dict[i];
   if (DOT) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -1302,11 +1314,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
     }
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     const int4* __restrict__ cj = reinterpret_cast<const int4*>(A.col) + (size_t)o0 * 32 + lane;
-    const unsigned* __restrict__ ij = reinterpret_cast<const unsigned*>(A.vidx) + (size_t)o0 * 32 + lane;
+    using IV = typename std::conditional<IB == 1, unsigned, uint2>::type;
+    const IV* __restrict__ ij = reinterpret_cast<const IV*>(A.vidx) + (size_t)o0 * 32 + lane;
 #pragma unroll 1
     for (int j0 = 0; j0 < w; j0 += U, cj += U * 32, ij += U * 32) {
       int4 c[U];
-      unsigned iv[U];
+      IV iv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (j0 + u < w) {
@@ -1320,7 +1333,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
       int allc = 0;
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (j0 + u < w) allc |= c[u].x | c[u].y | c[u].z | c[u].w | (int)(iv[u] >> 1);  // the index loads too: they go out with the columns
+        if (j0 + u < w) allc |= c[u].x | c[u].y | c[u].z | c[u].w | (int)(vi_bits(iv[u]) >> 1);  // the index loads too: they go out with the columns
       const int z = allc >> 31;
       double xv[U][4];
 #pragma unroll
@@ -1336,7 +1349,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
       for (int u = 0; u < U; ++u)
         if (j0 + u < w) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(s_dict[(iv[u] >> (8 * k)) & 0xffu], xv[u][k]));
+          for (int k = 0; k < 4; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(s_dict[vi_index(iv[u], k)], xv[u][k]));
         }
     }
     // epilogue, two rows at a time: their operand loads first (L1 hits, requested before the entry loop), then arithmetic and stores

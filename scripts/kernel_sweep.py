@@ -62,6 +62,8 @@ ENVS = {
     "auto-vi1": dict(PAMG_VI_VARIANT="1"),         # value-indexed kernel <U 8, 2 CTAs/SM>
     "auto-vi2": dict(PAMG_VI_VARIANT="2"),         # software-pipelined value-indexed kernel
     "auto-vi3": dict(PAMG_VI_VARIANT="3"),         # four interleaved rows per lane
+    "auto-vi8only": dict(PAMG_VALUE_INDEX="1"),    # one-byte indices only (no wide dictionaries on the coarse levels)
+    "auto-vi0": dict(PAMG_VI_VARIANT="0"),         # two rows per lane
     "auto-vi-sorted": dict(PAMG_SELL_SORT_FILL="1.25"),
     "auto-vi2-sorted": dict(PAMG_VI_VARIANT="2", PAMG_SELL_SORT_FILL="1.25"),
     "auto-pf1": dict(PAMG_SELL_PF="1"),
