@@ -397,13 +397,14 @@ def measure(workload, args, rank, world, local_rank, steps, warmup, headline):
     # one byte per entry, no row pointers) moves 5 B per entry.  The roofline fraction is taken on the bytes of the format that runs;
     # the fp64-CSR-equivalent rate is reported beside it.
     vi_a0 = bool(stt.value_indexed[0] & 1)
-    spmv_bytes = (5 * nnz_oo + 16 * n_own) if vi_a0 else csr_bytes
+    vi_wide = bool(stt.value_indexed[0] & 8)        # two index bytes (256 .. 4095 distinct values)
+    spmv_bytes = ((6 if vi_wide else 5) * nnz_oo + 16 * n_own) if vi_a0 else csr_bytes
     algo = {0: ("spmv A0", spmv_bytes, csr_bytes), 1: ("jacobi sweep A0", spmv_bytes + 16 * n_own, csr_bytes + 16 * n_own)}
     for kind, (name, nbytes, eq) in algo.items():
         ms = c.time_kernel(kind, 0, 13, True)[3:]
         kern[name] = dict(ms=float(np.mean(ms)), gbs=nbytes / (float(np.mean(ms)) * 1e-3) / 1e9, bytes=int(nbytes),
                           fp64_csr_equivalent_gbs=eq / (float(np.mean(ms)) * 1e-3) / 1e9, fp64_csr_equivalent_bytes=int(eq))
-    kname = {L.FORMAT_SELL: ("k_spmv_sell_vi4<MUL> (value-indexed SELL-C-sigma: int32 column + 1 byte into a dictionary of the distinct fp64 "
+    kname = {L.FORMAT_SELL: (f"k_spmv_sell_vi4<MUL> (value-indexed SELL-C-sigma: int32 column + {2 if vi_wide else 1} byte(s) into a dictionary of the distinct fp64 "
                              "values, C=128, 128-bit column loads, 4 interleaved rows per lane, persistent CTAs)") if vi_a0 else
              "k_spmv_sell<RPT=2,MUL> (SELL-C-sigma, C=64, 128-bit value loads, persistent CTAs)",
              L.FORMAT_STREAM: "k_spmv_stream<MUL> (CSR-stream, 128-bit coalesced loads, smem-staged products)"}.get(
@@ -452,7 +453,7 @@ def measure(workload, args, rank, world, local_rank, steps, warmup, headline):
                 roofline=dict(bound="hbm", kernel=kname + " level 0: y = A x, fp64 arithmetic / int32 columns", achieved=dom["gbs"],
                               peak=peak, unit="GB/s", frac=dom["gbs"] / peak, peak_source=peak_src, traffic=ncu_traffic(workload, args.gpus),
                               algorithmic_bytes_per_launch=dom["bytes"], ms_per_launch=dom["ms"],
-                              frac_of_nominal_8TBs=dom["gbs"] / 8000.0, value_indexed=vi_a0,
+                              frac_of_nominal_8TBs=dom["gbs"] / 8000.0, value_indexed=vi_a0, index_bytes=(2 if vi_wide else 1) if vi_a0 else 0,
                               fp64_csr_equivalent=dict(bytes_per_launch=dom["fp64_csr_equivalent_bytes"], gbs=dom["fp64_csr_equivalent_gbs"],
                                                        frac=dom["fp64_csr_equivalent_gbs"] / peak,
                                                        note="SURVEY 8(d) bytes of the same product with 12 B per entry; > 1 means fewer bytes cross the pins than a CSR fp64 kernel needs")),
@@ -574,7 +575,8 @@ def main():
                 r2 = dict(config=config_of(name, w2, args.gpus, r2["iters"], r2["levels"]), value=r2["value"], unit="DOF/s",
                           ms_per_step=r2["ms_per_step"], vcycle_ms=r2["vcycle_ms"], e2e=r2["e2e"], roofline=r2["roofline"],
                           kernels=r2["kernels"], cpu_baseline=r2["cpu_baseline"], parity=r2["parity"],
-                          true_residual_rel=r2["true_residual_rel"], host_setup_s=r2["host_setup_s"], gpu_launches=r2["gpu_launches"])
+                          true_residual_rel=r2["true_residual_rel"], host_setup_s=r2["host_setup_s"], gpu_launches=r2["gpu_launches"],
+                          **({"krylov": r2["krylov"]} if "krylov" in r2 else {}))
             secondary[name] = r2
 
     if rank == 0:
