@@ -553,6 +553,7 @@ struct Engine::Impl {
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
   int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
+  bool vi_ahead = false;    // 128-row value-indexed kernel, persistent launches: next slice's extents one iteration early + L2 prefetch (env PAMG_VI_AHEAD)
   int vi_variant = VI_DEFAULT_VARIANT;  // value-indexed SELL kernel (3 = four interleaved rows per lane): 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM>, 2 = software-pipelined (env PAMG_VI_VARIANT)
   int p_kernel = 0;         // SELL instantiation of the prolongators (launch_sell short_variant; env PAMG_P_KERNEL; measured: no gain)
   int64_t launches = 0;
@@ -730,7 +731,9 @@ void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, 
     if (vi && rpt == 2 && !try_unified) {  // value-indexed operator: its own kernel (the experimental variants below do not apply)
       *was_unified = false;
       using KernVi = void (*)(SellViView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
-      KernVi kv = vi_variant == 4   ? (KernVi)k_spmv_sell_vi4<MD, DT, 2>
+      KernVi kv = vi_variant == 6   ? (KernVi)k_spmv_sell_vi4<MD, DT, 2, 4, 3, 1>
+                  : vi_variant == 5 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1, 4, 3, 1>
+                  : vi_variant == 4 ? (KernVi)k_spmv_sell_vi4<MD, DT, 2>
                   : vi_variant == 3 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1>
                   : vi_variant == 2 ? (KernVi)k_spmv_sell_vi_pipe<MD, DT>
                   : vi_variant == 1 ? (KernVi)k_spmv_sell_vi<MD, DT, 8, 2>
@@ -887,7 +890,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     if (m.sell_rpt)
       launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
                   try_unified, I.unified_mode, &was_unified, (m.sell_vi || use_vi4) ? &viv : nullptr,
-                  use_vi4 ? (m.vi4_ib == 2 ? 4 : 3) : (I.vi_variant == 3 ? 0 : I.vi_variant));  // blocks without the 128-row layout (sorted rows): two rows per lane
+                  use_vi4 ? (m.vi4_ib == 2 ? 4 : 3) + (I.vi_ahead && L.bounded ? 2 : 0) : (I.vi_variant == 3 ? 0 : I.vi_variant));  // blocks without the 128-row layout (sorted rows): two rows per lane
     else if (m.stream)
       launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
@@ -972,6 +975,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   I.have_ipc.assign(I.nparts, 0);
   const pamg_options& o = h->opts;
   if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
+  if (const char* va = getenv("PAMG_VI_AHEAD")) I.vi_ahead = atoi(va) != 0;
   if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(3, atoi(vv)));
 
   // global decisions (identical in every process because the metadata is replicated)

@@ -1268,7 +1268,10 @@ __device__ __forceinline__ unsigned vi_index(const uint2& v, int k) { return ((k
 __device__ __forceinline__ unsigned vi_bits(unsigned v) { return v; }
 __device__ __forceinline__ unsigned vi_bits(const uint2& v) { return v.x | v.y; }
 
-template <int MODE, bool DOT, int IB = 1, int U = 4, int MINB = 3>
+// AHEAD = 1: the extents of a warp's NEXT slice are loaded one iteration early and that slice's columns / indices are requested into L2
+// (prefetch.global.L2: no register, no scoreboard), which takes the extents latency off the per-slice chain and turns the column latency
+// from HBM into L2.
+template <int MODE, bool DOT, int IB = 1, int U = 4, int MINB = 3, int AHEAD = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, const double* __restrict__ x, EpiArgs a, DevState* st, FusedHalo fh,
                                                             double* partials, RedCtx rc, int publish, int red_slot) {
   if (st->done) return;
@@ -1294,8 +1297,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = BLOCK / 32;
-  for (int sl = bid * wpb + (threadIdx.x >> 5); sl < A.nslices; sl += n_main * wpb) {
-    const int o0 = A.slice_off[sl], w = A.slice_off[sl + 1] - o0;
+  const int stride = n_main * wpb;
+  int sl = bid * wpb + (threadIdx.x >> 5);
+  int o0c = 0, wc = 0;  // AHEAD: extents of the current slice, loaded during the previous iteration
+  if (AHEAD && sl < A.nslices) {
+    o0c = A.slice_off[sl];
+    wc = A.slice_off[sl + 1] - o0c;
+  }
+  for (; sl < A.nslices; sl += stride) {
+    int o0, w;
+    if (AHEAD) {
+      o0 = o0c;
+      w = wc;
+      if (sl + stride < A.nslices) {
+        o0c = A.slice_off[sl + stride];
+        wc = A.slice_off[sl + stride + 1] - o0c;
+      } else {
+        wc = 0;
+      }
+    } else {
+      o0 = A.slice_off[sl];
+      w = A.slice_off[sl + 1] - o0;
+    }
     const int base = sl * 128;
     const bool full = base + 128 <= A.nrows;
     // row of (lane, k): 32 apart in a full slice, adjacent in the partial last one
@@ -1351,6 +1374,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_spmv_sell_vi4(SellViView A, con
 #pragma unroll
           for (int k = 0; k < 4; ++k) s[k] = __dadd_rn(s[k], __dmul_rn(s_dict[vi_index(iv[u], k)], xv[u][k]));
         }
+    }
+    if (AHEAD && wc > 0) {  // next slice of this warp: one 128-byte line per lane and request (columns: 4 lines per entry, indices: IB)
+      const char* pc = reinterpret_cast<const char*>(A.col) + (size_t)o0c * 512;
+      const char* pi = reinterpret_cast<const char*>(A.vidx) + (size_t)o0c * (128 * IB);
+      for (int q = lane; q < wc * 4; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + (size_t)q * 128));
+      for (int q = lane; q < wc * IB; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + (size_t)q * 128));
     }
     // epilogue, two rows at a time: their operand loads first (L1 hits, requested before the entry loop), then arithmetic and stores
     double contrib = 0.0;
