@@ -779,6 +779,7 @@ bool gpu_aggregate(const GpuMat* A, const int32_t* owner, const int32_t* pos, co
   // small level or one with long rows (Galerkin matrices: 30-70 strong neighbours, 900-4900 vertices within distance 2) is
   // done sooner by the host's single walk.  force: tests (PAMG_GPU_AGG=2).
   if (!force && (n < 1000000 || A->nnz > 12 * n)) return false;
+  if (!force && n > 64000000) return false;  // measured and parity-tested up to 256^3 (16.8 M vertices); 512^3 keeps the host walk
   const int g_n = (int)((n + TB - 1) / TB), g_n1 = (int)((n + 1 + TB - 1) / TB);
   Buf<int32_t> d_owner, d_pos;
   d_owner.upload(owner, (size_t)n);
