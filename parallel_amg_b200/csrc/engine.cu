@@ -553,6 +553,7 @@ struct Engine::Impl {
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
   int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
+  bool vi_persist_long = false;  // long-row value-indexed blocks (level-1 A) as one resident wave too, so that the look-ahead applies (env PAMG_VI_PERSIST_LONG)
   bool vi_ahead = true;     // 128-row value-indexed kernel, persistent launches: next slice's extents one iteration early + L2 prefetch
                             // (env PAMG_VI_AHEAD=0 turns it off; 256^3: solve 34.03 -> 33.58 ms, Jacobi sweep 0.221 -> 0.209 ms, plain SpMV 0.159 -> 0.162)
   int vi_variant = VI_DEFAULT_VARIANT;  // value-indexed SELL kernel (3 = four interleaved rows per lane): 0 = <U 4, 3 CTAs/SM>, 1 = <U 8, 2 CTAs/SM>, 2 = software-pipelined (env PAMG_VI_VARIANT)
@@ -871,7 +872,8 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     // PAMG_SELL_PF bit mask: 1 = P, 2 = A with long rows, 4 = R (these then run persistent, which the prefetch needs)
     const int pf_bit = op.which == PAMG_P_OO ? 1 : op.which == PAMG_R_OO ? 4 : (mean_nnz > 12.0 ? 2 : 0);
     const bool prefetch = I.persistent && m.sell_rpt == 2 && (I.sell_pf & pf_bit) && !op.dot && !try_unified;
-    const bool bounded = I.persistent && m.sell_rpt && (mean_nnz <= 12.0 || try_unified || prefetch);
+    const bool vi4_here = m.sell_vi4 && I.vi_variant == 3 && !try_unified;
+    const bool bounded = I.persistent && m.sell_rpt && (mean_nnz <= 12.0 || try_unified || prefetch || (vi4_here && I.vi_persist_long));
     LaunchArgs L{0, bounded || op.dot, pd.stream, xin[i], epi[i], pd.st.p, fh, pd.partials.p, pd.rc, publish, op.slot};
     L.fh.v = xin[i];
     int n_main;
@@ -977,6 +979,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   const pamg_options& o = h->opts;
   if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
   if (const char* va = getenv("PAMG_VI_AHEAD")) I.vi_ahead = atoi(va) != 0;
+  if (const char* vp = getenv("PAMG_VI_PERSIST_LONG")) I.vi_persist_long = atoi(vp) != 0;
   if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(3, atoi(vv)));
 
   // global decisions (identical in every process because the metadata is replicated)

@@ -40,6 +40,15 @@ def kernel_sweep():
     txt += sweep_rows(os.path.join(G, "r3_sweep_vi3.json"), ("auto-vi3",), {"auto-vi3": "variant 3: FOUR interleaved rows per lane, loads pinned by a data dependence"})
     txt += sweep_rows(os.path.join(G, "r3_sweep_vi4.json"), ("auto-vi8only", "auto"),
                       {"auto-vi8only": "variant 3, one-byte indices only (PAMG_VALUE_INDEX=1)", "auto": "**shipped default**: variant 3 + two-byte indices for A1 (285..2000 distinct values)"})
+    txt += ["", "## Look-ahead and level-1 options (same code, later boxes)", ""] + hdr
+    txt += sweep_rows(os.path.join(G, "r3_sweep_vi5.json"), ("auto", "auto-ahead"),
+                      {"auto": "variant 3 without look-ahead", "auto-ahead": "**shipped**: + extents one iteration early, L2 prefetch of the next slice (PAMG_VI_AHEAD=1)"})
+    txt += sweep_rows(os.path.join(G, "r3_sweep_vi6.json"), ("auto", "auto-plong", "auto-w512", "auto-renum", "auto-plong-w512"),
+                      {"auto": "shipped defaults (another box)", "auto-plong": "level-1 A as one resident wave + look-ahead (PAMG_VI_PERSIST_LONG=1)",
+                       "auto-w512": "coarse rows renumbered by length, window 512 (PAMG_RENUMBER=1)", "auto-renum": "renumbered, window 4096",
+                       "auto-plong-w512": "both"})
+    txt += ["", "None of the level-1 options pays: with two-byte indices the padding of A1 costs 6 bytes per entry, and the renumbering that removes it (fill 1.159 -> 1.006) "
+            "scatters the x gathers of A1 and the columns of P0 / R0 (L1 SpMV 0.146 -> 0.179 ms).", ""]
     txt += ["", "## Reading", "",
             "* The 7-point Poisson matrix has 2 distinct values, its smoothed-aggregation P and R 9, the level-1 Galerkin matrix a few hundred to two thousand; "
             "the Q1 elasticity matrix of config 4 has 22, the jump-coefficient matrix of config 5 20 (P: 51, coarse levels 1100-1500). "
