@@ -45,7 +45,11 @@ enum { PAMG_CYCLE_V = 0, PAMG_CYCLE_W = 1 };
  * the contiguous val/col ranges, products staged in shared memory); the storage is plain CSR for both.
  * SELL = SELL-C-sigma (C = 32 x sell_rows_per_thread rows per slice, column-major slices, rows sorted by
  * length inside windows of sell_sigma rows), one thread per row, no row pointers.  AUTO decides per
- * operator from the nnz/row distribution (padding of the SELL layout; row length vs. the STREAM buffer). */
+ * operator from the nnz/row distribution (padding of the SELL layout; row length vs. the STREAM buffer).
+ * A SELL block (2 rows per thread) with at most 255 distinct values -- stencil matrices, their prolongators -- is stored
+ * VALUE-INDEXED: int32 column + one byte into a dictionary of the original doubles (two bytes up to 4095 values), four
+ * interleaved rows per lane in slices of 128 rows: 5 (6) instead of 12 bytes per entry, bit-identical products and sums
+ * (pamg_stats.value_indexed, pamg_layout_sell_values; env PAMG_VALUE_INDEX=0 keeps fp64 values). */
 enum { PAMG_FORMAT_AUTO = 0, PAMG_FORMAT_CSR = 1, PAMG_FORMAT_STREAM = 2, PAMG_FORMAT_SELL = 3 };
 /* blocks of the split (own/ghost) storage of a level, PSparseMatrix own_own_values /
  * own_ghost_values (SURVEY.md App. A "PSparseMatrix") */

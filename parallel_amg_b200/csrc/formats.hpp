@@ -49,7 +49,10 @@ inline bool value_dictionary(const LocalCsr& m, std::vector<double>& dict, int m
     bool have_last = false;
 #pragma omp for schedule(static)
     for (int64_t k = 0; k < nnz; ++k) {
-      if (too_many) continue;
+      bool stop;
+#pragma omp atomic read
+      stop = too_many;
+      if (stop) continue;
       const uint64_t b = bits(m.val[k]);
       if (have_last && b == last) continue;
       last = b;

@@ -5,7 +5,9 @@
 //   a2 smoothing       out = x + w (b - A x)           (+ fused dot(r, z) on level 0)
 //   a3 residual        out = b - A x ;  restrict  b_c = R r  (+ fused coarse pre-smooth x_c = w_c b_c)
 //   a4 prolong+correct out = x + P e_c
-// so one templated kernel family (three storage formats) covers them.
+// so one templated kernel family (three storage formats) covers them.  Operators with few distinct values (the three
+// BASELINE matrices and their prolongators) run the value-indexed SELL kernels (k_spmv_sell_vi4: int32 column + index
+// byte(s) into a dictionary of the original doubles, 5-6 instead of 12 bytes per entry, same bits).
 //
 // Halo exchange (PartitionedArrays mul!: start consistent!(b); c_own = A_oo b_own; wait;
 // c_own += A_og b_ghost) is FUSED INTO THE SAME KERNEL as three CTA roles:
