@@ -205,10 +205,10 @@ int pamg_get_diag(pamg_ctx* c, int32_t level, int32_t part, double* diag, double
 int pamg_layout_sell(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
                      int64_t* n_slices, int64_t* stored, int32_t* permuted, int32_t* slice_off, int32_t* col,
                      double* val, int32_t* perm);
-/* value-indexed SELL storage of the same block: *indexed = 1 when it has at most 255 distinct non-zero values (bit patterns), then
- * dict[256] (dict[0] = +0.0, the padding value; ascending bit pattern behind it; unused entries 0.0) and vidx[stored] with
- * dict[vidx[k]] == val[k] bit for bit in the layout of pamg_layout_sell.  The device stores such blocks as int32 column +
- * one byte per entry (kernels.cuh k_spmv_sell_vi); env PAMG_VALUE_INDEX=0 keeps the fp64 values. */
+/* value-indexed SELL storage of the same block: *indexed = 1 when it has at most 255 distinct non-zero values (bit patterns), 2 when at
+ * most 4095 (two index bytes, little endian), else 0.  dict[4096] (dict[0] = +0.0, the padding value; ascending bit pattern behind it;
+ * unused entries 0.0) and vidx[*indexed x stored] with dict[index k] == val[k] bit for bit in the layout of pamg_layout_sell.  The device
+ * stores such blocks as int32 column + index byte(s) per entry (kernels.cuh k_spmv_sell_vi4); env PAMG_VALUE_INDEX=0 keeps fp64 values. */
 int pamg_layout_sell_values(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t rows_per_slice, int32_t sigma,
                             int32_t* indexed, int64_t* stored, double* dict, uint8_t* vidx);
 int pamg_layout_stream(pamg_ctx* c, int32_t level, int32_t part, int32_t which, int32_t max_rows, int32_t max_entries,

@@ -373,15 +373,16 @@ class Context:
         return dict(slice_off=off, col=col, val=val, perm=perm, permuted=bool(pm.value), C=rows_per_slice)
 
     def layout_sell_values(self, level, part, which, rows_per_slice=64, sigma=1):
-        """(dict[256], vidx[stored]) of the value-indexed SELL storage, or None when the block has more than 255 distinct values."""
+        """(dict[4096], vidx[stored] as uint8 or uint16) of the value-indexed SELL storage, or None when the block has more than 4095
+        distinct values; vidx.dtype tells the index width."""
         ix, st = C.c_int32(), C.c_int64()
         self._ck(self.lib.pamg_layout_sell_values(self._h, level, part, which, rows_per_slice, sigma, C.byref(ix), C.byref(st), None, None))
         if not ix.value:
             return None
-        d, v = np.zeros(256), np.zeros(st.value, np.uint8)
+        d, v = np.zeros(4096), np.zeros(st.value * ix.value, np.uint8)
         self._ck(self.lib.pamg_layout_sell_values(self._h, level, part, which, rows_per_slice, sigma, C.byref(ix), C.byref(st),
                                                   _ptr(d, C.c_double), _ptr(v, C.c_uint8)))
-        return d, v
+        return d, (v if ix.value == 1 else v.view("<u2"))
 
     def layout_stream(self, level, part, which, max_rows=1024, max_entries=3069):
         nb = C.c_int64()

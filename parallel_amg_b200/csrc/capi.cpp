@@ -345,16 +345,20 @@ int pamg_layout_sell_values(pamg_ctx* c, int32_t level, int32_t part, int32_t wh
     need(which == PAMG_A_OO || which == PAMG_P_OO || which == PAMG_R_OO, "SELL applies to own-own blocks");
     need(rows_per_slice >= 1 && rows_per_slice <= 1024 && indexed && stored, "bad arguments");
     SellHost sh;
-    const bool ok = value_dictionary(pl.blk[which], sh.dict);
-    *indexed = ok ? 1 : 0;
+    int ib = value_dictionary(pl.blk[which], sh.dict, 255) ? 1 : 0;
+    if (!ib && value_dictionary(pl.blk[which], sh.dict, 4095)) ib = 2;  // the wide form of the 128-row kernel
+    *indexed = ib;
     const int inter = sigma < 0 ? -sigma : 0;
-    sell_layout(pl.blk[which], rows_per_slice, inter ? 1 : sigma, sh, ok && vidx != nullptr, inter);
+    sell_layout(pl.blk[which], rows_per_slice, inter ? 1 : sigma, sh, ib && vidx != nullptr, inter);
     *stored = (int64_t)sh.off[sh.off.size() - 1] * rows_per_slice;
-    if (!ok) return PAMG_OK;
-    if (dict) std::memcpy(dict, sh.dict.data(), 256 * sizeof(double));
+    if (!ib) return PAMG_OK;
+    if (dict) {
+      std::memset(dict, 0, 4096 * sizeof(double));
+      std::memcpy(dict, sh.dict.data(), sh.dict.size() * sizeof(double));
+    }
     if (vidx) {
-      sell_value_index(sh, 1);
-      std::memcpy(vidx, sh.vidx.data(), (size_t)*stored);
+      sell_value_index(sh, ib);
+      std::memcpy(vidx, sh.vidx.data(), (size_t)*stored * (size_t)ib);
     }
     return PAMG_OK;
   });

@@ -125,30 +125,32 @@ def test_value_indexed_sell_storage(ctx, C, sigma):
     """kernels.cuh k_spmv_sell_vi reads dict[vidx[k]] instead of val[k]: the dictionary must reproduce every stored value BIT FOR BIT
     (padding -> entry 0 = +0.0), hold <= 255 distinct non-zero patterns in ascending pattern order, and blocks with more distinct values
     (the Galerkin matrices of the coarse levels) must be reported as not indexable."""
-    seen_yes = seen_no = 0
+    seen = {1: 0, 2: 0, 0: 0}
     for l, p, which in blocks(ctx):
         lay = ctx.layout_sell(l, p, which, C, sigma)
         vi = ctx.layout_sell_values(l, p, which, C, sigma)
         vals = ctx.block(l, p, which)[2]
         distinct = np.unique(vals.view(np.uint64))
         distinct = distinct[distinct != 0]
-        if len(distinct) > 255:
+        if len(distinct) > 4095:
             assert vi is None
-            seen_no += 1
+            seen[0] += 1
             continue
-        seen_yes += 1
         assert vi is not None
         d, idx = vi
+        width = 1 if len(distinct) <= 255 else 2
+        assert idx.dtype.itemsize == width
+        seen[width] += 1
         assert len(idx) == len(lay["val"])
         assert np.array_equal(d[idx].view(np.uint64), lay["val"].view(np.uint64))      # bit-identical values, padding included
         assert d.view(np.uint64)[0] == 0
         used = d.view(np.uint64)[1:1 + len(distinct)]
         assert np.array_equal(used, distinct) and np.all(d.view(np.uint64)[1 + len(distinct):] == 0)
-    assert seen_yes >= 3 and seen_no >= 1      # level 0 of Poisson has 2 / 9 / 9 distinct values; level 1 has hundreds
+    assert seen[1] >= 3 and seen[2] >= 1     # level 0 of Poisson has 2 / 9 / 9 distinct values; coarse-level blocks have hundreds
 
 
 def test_value_dictionary_keeps_signed_zero_and_counts_exactly():
-    """-0.0 is a value of its own (its products keep their sign); exactly 255 distinct non-zero values still fit, 256 do not."""
+    """-0.0 is a value of its own (its products keep their sign); exactly 255 distinct non-zero values still fit one byte, 256 need two."""
     for ndist, expect in ((255, True), (256, False)):
         n = 600
         off = np.ones(n - 1)                                                   # distinct patterns: 1.0, 2 .. k, -0.0, the diagonal = k + 2
@@ -163,8 +165,8 @@ def test_value_dictionary_keeps_signed_zero_and_counts_exactly():
         c.set_matrix_global(A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64), np.zeros(n, np.int32))
         c.setup(c.default_options(coarse_size=10 ** 6))                      # single level: the block is the matrix
         vi = c.layout_sell_values(0, 0, L.A_OO, 64, 1)
-        assert (vi is not None) == expect
-        if expect:
+        assert vi is not None and (vi[1].dtype.itemsize == 1) == expect
+        if True:
             d, idx = vi
             lay = c.layout_sell(0, 0, L.A_OO, 64, 1)
             assert np.array_equal(d[idx].view(np.uint64), lay["val"].view(np.uint64))
