@@ -166,8 +166,7 @@ def test_value_dictionary_keeps_signed_zero_and_counts_exactly():
         c.setup(c.default_options(coarse_size=10 ** 6))                      # single level: the block is the matrix
         vi = c.layout_sell_values(0, 0, L.A_OO, 64, 1)
         assert vi is not None and (vi[1].dtype.itemsize == 1) == expect
-        if True:
-            d, idx = vi
-            lay = c.layout_sell(0, 0, L.A_OO, 64, 1)
-            assert np.array_equal(d[idx].view(np.uint64), lay["val"].view(np.uint64))
-            assert (d.view(np.uint64) == np.float64(-0.0).view(np.uint64)).sum() == 1
+        d, idx = vi
+        lay = c.layout_sell(0, 0, L.A_OO, 64, 1)
+        assert np.array_equal(d[idx].view(np.uint64), lay["val"].view(np.uint64))
+        assert (d.view(np.uint64) == np.float64(-0.0).view(np.uint64)).sum() == 1
