@@ -553,6 +553,9 @@ struct Engine::Impl {
   bool stream_long = true;  // CSR-stream blocks with long rows use 16 lanes per row in phase B (env PAMG_STREAM_LONG=0: one thread per row)
   int unified_mode = 1;     // 1: every CTA packs + boundary own/ghost split; 2 ("lite", env PAMG_UNIFIED_MODE): pack CTAs + boundary role behind the slices
   int sell_pf = 0;          // persistent SELL launches with an L2 prefetch two slices ahead: bit mask 1 P, 2 long-row A, 4 R (env PAMG_SELL_PF)
+  int vi_occ = 2;           // one-byte value-indexed kernel, persistent launches (short rows): 2 = U = 2 at 64 registers / 4 CTAs per SM (shipped:
+                            // 256^3 solve 33.7 -> 31.4 ms, SpMV 0.163 -> 0.144 ms), 0 = U = 4 at 80 registers / 3 CTAs, 1 = U = 4 squeezed into 64
+                            // registers (spills: 40.3 ms); env PAMG_VI_OCC
   bool vi_persist_long = false;  // long-row value-indexed blocks (level-1 A) as one resident wave too, so that the look-ahead applies (env PAMG_VI_PERSIST_LONG)
   bool vi_ahead = true;     // 128-row value-indexed kernel, persistent launches: next slice's extents one iteration early + L2 prefetch
                             // (env PAMG_VI_AHEAD=0 turns it off; 256^3: solve 34.03 -> 33.58 ms, Jacobi sweep 0.221 -> 0.209 ms, plain SpMV 0.159 -> 0.162)
@@ -726,14 +729,16 @@ void launch_stream(int mode, bool dot, bool long_rows, StreamView A, const Launc
 // try_unified: fused launch of one part per GPU -- run without role CTAs when every CTA's share of the boundary rows fits
 // (kernels.cuh "Unified CTA roles"); *was_unified reports the decision.
 void launch_sell(int mode, bool dot, int rpt, int short_variant, bool prefetch, SellView A, LaunchArgs L, bool try_unified,
-                 int unified_mode, bool* was_unified, const SellViView* vi = nullptr, int vi_variant = 0) {
+                 int unified_mode, bool* was_unified, const SellViView* vi = nullptr, int vi_variant = 0, int vi_occ = 0) {
   dispatch_mode(mode, dot, [&](auto md, auto dt) {
     constexpr int MD = decltype(md)::value;
     constexpr bool DT = decltype(dt)::value;
     if (vi && rpt == 2 && !try_unified) {  // value-indexed operator: its own kernel (the experimental variants below do not apply)
       *was_unified = false;
       using KernVi = void (*)(SellViView, const double*, EpiArgs, DevState*, FusedHalo, double*, RedCtx, int, int);
-      KernVi kv = vi_variant == 6   ? (KernVi)k_spmv_sell_vi4<MD, DT, 2, 4, 3, 1>
+      KernVi kv = vi_variant == 5 && vi_occ == 1 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1, 4, 4, 1>   // 64 registers (spills), 4 CTAs/SM
+                  : vi_variant == 5 && vi_occ == 2 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1, 2, 4, 1> // U = 2, 64 registers, 4 CTAs/SM
+                  : vi_variant == 6 ? (KernVi)k_spmv_sell_vi4<MD, DT, 2, 4, 3, 1>
                   : vi_variant == 5 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1, 4, 3, 1>
                   : vi_variant == 4 ? (KernVi)k_spmv_sell_vi4<MD, DT, 2>
                   : vi_variant == 3 ? (KernVi)k_spmv_sell_vi4<MD, DT, 1>
@@ -893,7 +898,7 @@ void Engine::enqueue_op(const OpSpec& op, const std::vector<const double*>& xin,
     if (m.sell_rpt)
       launch_sell(op.mode, op.dot, m.sell_rpt, (op.which == PAMG_P_OO && m.short_rows) ? I.p_kernel : 0, prefetch, m.slview(), L,
                   try_unified, I.unified_mode, &was_unified, (m.sell_vi || use_vi4) ? &viv : nullptr,
-                  use_vi4 ? (m.vi4_ib == 2 ? 4 : 3) + (I.vi_ahead && L.bounded ? 2 : 0) : (I.vi_variant == 3 ? 0 : I.vi_variant));  // blocks without the 128-row layout (sorted rows): two rows per lane
+                  use_vi4 ? (m.vi4_ib == 2 ? 4 : 3) + (I.vi_ahead && L.bounded ? 2 : 0) : (I.vi_variant == 3 ? 0 : I.vi_variant), I.vi_occ);  // blocks without the 128-row layout (sorted rows): two rows per lane
     else if (m.stream)
       launch_stream(op.mode, op.dot, I.stream_long && mean_nnz >= 48.0, m.sview(), L);
     else
@@ -980,6 +985,7 @@ Engine::Engine(Hierarchy* h, int nlocal, const int32_t* local_parts, const int32
   if (const char* pk = getenv("PAMG_P_KERNEL")) I.p_kernel = std::max(0, std::min(2, atoi(pk)));
   if (const char* va = getenv("PAMG_VI_AHEAD")) I.vi_ahead = atoi(va) != 0;
   if (const char* vp = getenv("PAMG_VI_PERSIST_LONG")) I.vi_persist_long = atoi(vp) != 0;
+  if (const char* vo = getenv("PAMG_VI_OCC")) I.vi_occ = std::max(0, std::min(2, atoi(vo)));
   if (const char* vv = getenv("PAMG_VI_VARIANT")) I.vi_variant = std::max(0, std::min(3, atoi(vv)));
 
   // global decisions (identical in every process because the metadata is replicated)

@@ -64,6 +64,8 @@ ENVS = {
     "auto-vi3": dict(PAMG_VI_VARIANT="3"),         # four interleaved rows per lane
     "auto-ahead": dict(PAMG_VI_AHEAD="1"),
     "auto-noahead": dict(PAMG_VI_AHEAD="0"),
+    "auto-occ1": dict(PAMG_VI_OCC="1"),            # one-byte value-indexed kernel at 64 registers / 4 CTAs per SM (U = 4, spills)
+    "auto-occ2": dict(PAMG_VI_OCC="2"),            # ... U = 2, no spills
     "auto-plong": dict(PAMG_VI_PERSIST_LONG="1"),  # level-1 A (value-indexed, 31 entries per row) as one resident wave + look-ahead
     "auto-plong-w512": dict(PAMG_VI_PERSIST_LONG="1", PAMG_RENUMBER="1", PAMG_RENUMBER_WINDOW="512"),         # extents one iteration early + L2 prefetch of the next slice
     "auto-vi8only": dict(PAMG_VALUE_INDEX="1"),    # one-byte indices only (no wide dictionaries on the coarse levels)
@@ -85,7 +87,7 @@ else:
     CONFIGS = {k: v for k, v in CONFIGS.items() if k not in ENVS}
 res = {}
 for name, kw in CONFIGS.items():
-    for k in ("PAMG_VI_PERSIST_LONG", "PAMG_VI_AHEAD", "PAMG_VALUE_INDEX", "PAMG_VI_VARIANT", "PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW", "PAMG_STREAM_LONG", "PAMG_P_SIGMA", "PAMG_R_SIGMA", "PAMG_SELL_PF"):
+    for k in ("PAMG_VI_OCC", "PAMG_VI_PERSIST_LONG", "PAMG_VI_AHEAD", "PAMG_VALUE_INDEX", "PAMG_VI_VARIANT", "PAMG_P_KERNEL", "PAMG_RENUMBER", "PAMG_SELL_SORT_FILL", "PAMG_RENUMBER_WINDOW", "PAMG_STREAM_LONG", "PAMG_P_SIGMA", "PAMG_R_SIGMA", "PAMG_SELL_PF"):
         os.environ.pop(k, None)
     os.environ.update(ENVS.get(name, {}))
     c.set_kernel_options(**kw)
