@@ -14,13 +14,13 @@ KEYS = ['L0.spmv', 'L0.jacobi', 'L0.resid+restrict', 'L0.prolong', 'L0.spmv+dot'
         'L1.resid+restrict', 'L1.prolong']
 
 
-def sweep_rows(path, only=None, rename=None):
+def sweep_rows(path, only=None, rename=None, keys=None):
     d = json.load(open(path))
     out = []
     for name in (only or list(d)):
         row = d[name]
-        out.append(f"| {(rename or {}).get(name, name)} | {row['solve_ms']:.2f} | {row['vcycle_ms']:.3f} | " +
-                   " | ".join(f"{row[k]['ms']:.4f} / {row[k]['frac']:.2f}" for k in KEYS) + f" | {row.get('value_indexed')} |")
+        cells = [f"{row[k]['ms']:.4f} / {row[k]['frac']:.2f}" if k in row and (keys is None or k in keys) else "–" for k in KEYS]
+        out.append(f"| {(rename or {}).get(name, name)} | {row['solve_ms']:.2f} | {row['vcycle_ms']:.3f} | " + " | ".join(cells) + f" | {row.get('value_indexed')} |")
     return out
 
 
@@ -47,6 +47,9 @@ def kernel_sweep():
                       {"auto": "shipped defaults (another box)", "auto-plong": "level-1 A as one resident wave + look-ahead (PAMG_VI_PERSIST_LONG=1)",
                        "auto-w512": "coarse rows renumbered by length, window 512 (PAMG_RENUMBER=1)", "auto-renum": "renumbered, window 4096",
                        "auto-plong-w512": "both"})
+    txt += sweep_rows(os.path.join(G, "r3_sweep_vi7.json"), ("auto", "auto-occ1", "auto-occ2"),
+                      {"auto": "3 CTAs/SM (U = 4, 80 registers; level 0 only in this sweep)", "auto-occ1": "U = 4 squeezed into 64 registers, 4 CTAs/SM (spills in the loop)",
+                       "auto-occ2": "**shipped**: U = 2, 64 registers, 4 CTAs/SM, no spill (PAMG_VI_OCC=2)"}, keys=KEYS[:6])
     txt += ["", "None of the level-1 options pays: with two-byte indices the padding of A1 costs 6 bytes per entry, and the renumbering that removes it (fill 1.159 -> 1.006) "
             "scatters the x gathers of A1 and the columns of P0 / R0 (L1 SpMV 0.146 -> 0.179 ms).", ""]
     txt += ["", "## Reading", "",
@@ -61,7 +64,8 @@ def kernel_sweep():
             "(column load, its gathers, next column load, ...); `asm volatile(\"\" ::: \"memory\")` and `__syncwarp()` do not hold non-coherent loads back. "
             "What does: the gather index is offset by the sign of the OR of all the step's columns and indices (zero, but not provably): first run of variant 3 "
             "Jacobi 0.295 ms, with the dependence 0.2225 ms.",
-            "* Whole solve 43.1 -> 34.1 ms (random rhs, 22 iterations); with the benchmark's rhs (19 iterations) 37.6 -> 29.4 ms.", ""]
+            "* With the loads pinned, U = 2 fits 64 registers without a spill: 4 CTAs/SM, SpMV 0.163 -> 0.144 ms, solve 33.7 -> 31.4 ms (last table).",
+            "* Whole solve 43.1 -> 31.4 ms (random rhs, 22 iterations); with the benchmark's rhs (19 iterations) 37.6 -> 27.0 ms.", ""]
     open(os.path.join(P, "r03_kernel_sweep.md"), "w").write("\n".join(txt))
 
 
