@@ -105,6 +105,8 @@ void merge_staged(pamg_ctx* c) {
     auto& s = c->staged[src_part[g]];
     A.ptr[g + 1] = A.ptr[g] + (s.rowptr[src_row[g] + 1] - s.rowptr[src_row[g]]);
   }
+  huge_reserve(A.col, (size_t)A.ptr[n]);
+  huge_reserve(A.val, (size_t)A.ptr[n]);
   A.col.resize(A.ptr[n]);
   A.val.resize(A.ptr[n]);
   for (int64_t g = 0; g < n; ++g) {

@@ -7,12 +7,41 @@
 //   exchange plan of consistent!/assemble! -> PartLevel::{recv, send, send_idx}
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
+#ifdef __linux__
+#include <sys/mman.h>
+#endif
 
 #include "../../include/pamg.h"
 
 namespace pamg {
+
+// The setup allocates a few GB of fresh vectors (matrices of every level, global and split); their first touch costs a page fault
+// per 4 KB.  Where the kernel offers transparent huge pages on request (THP = madvise) a large buffer can be reserved first and
+// advised, so that the value-initialising resize / assign behind it faults in 2 MB steps.  MEASURED AND LEFT OFF: in the build
+// container 480 MB take 0.13-0.19 s instead of 0.31-0.42 s and the 160^3 host setup 4.1-4.9 s instead of 4.5-5.1 s, but on the GPU
+// box the 256^3 setup with the device chain went 8.96 -> 11.1 / 11.6 s (gpurun_out/r3_huge.log: the gallery halves, the phases
+// that move matrices through pinned staging lose more).  PAMG_HUGE_PAGES=1 turns the hint on.
+inline bool huge_pages_wanted() {
+  static const bool on = [] {
+    const char* e = std::getenv("PAMG_HUGE_PAGES");
+    return e && std::atoi(e) != 0;
+  }();
+  return on;
+}
+template <class T>
+inline void huge_reserve(std::vector<T>& v, size_t n) {
+  if (n * sizeof(T) < ((size_t)8 << 20) || v.capacity() >= n || !huge_pages_wanted()) return;
+  v.reserve(n);
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+  const uintptr_t two_mb = (uintptr_t)2 << 20;
+  const uintptr_t a = ((uintptr_t)v.data() + two_mb - 1) & ~(two_mb - 1);
+  const uintptr_t e = ((uintptr_t)v.data() + n * sizeof(T)) & ~(two_mb - 1);
+  if (e > a) (void)madvise((void*)a, e - a, MADV_HUGEPAGE);
+#endif
+}
 
 struct Csr {  // global matrix, global ids, sorted columns
   int64_t nrows = 0, ncols = 0;

@@ -91,6 +91,7 @@ static void stencil_matrix(int ndim, const int64_t* dims, Csr& A, RowFn rowfn) {
     n *= dims[a];
   }
   A.nrows = A.ncols = n;
+  huge_reserve(A.ptr, (size_t)n + 1);
   A.ptr.assign(n + 1, 0);
 #pragma omp parallel for schedule(static)
   for (int64_t g = 0; g < n; ++g) {
@@ -103,6 +104,8 @@ static void stencil_matrix(int ndim, const int64_t* dims, Csr& A, RowFn rowfn) {
     A.ptr[g + 1] = cnt;
   }
   for (int64_t g = 0; g < n; ++g) A.ptr[g + 1] += A.ptr[g];
+  huge_reserve(A.col, (size_t)A.ptr[n]);
+  huge_reserve(A.val, (size_t)A.ptr[n]);
   A.col.resize(A.ptr[n]);
   A.val.resize(A.ptr[n]);
 #pragma omp parallel for schedule(static)
@@ -192,6 +195,7 @@ void gallery_elasticity(const int64_t* dims, double E, double nu, Csr& A, std::v
     }
   const int64_t nn = nx * ny * nz, n = 3 * nn;
   A.nrows = A.ncols = n;
+  huge_reserve(A.ptr, (size_t)n + 1);
   A.ptr.assign(n + 1, 0);
   coords.resize(3 * nn);
 #pragma omp parallel for schedule(static)
@@ -208,6 +212,8 @@ void gallery_elasticity(const int64_t* dims, double E, double nu, Csr& A, std::v
     for (int d = 0; d < 3; ++d) A.ptr[3 * v + d + 1] = 3 * cnt;
   }
   for (int64_t r = 0; r < n; ++r) A.ptr[r + 1] += A.ptr[r];
+  huge_reserve(A.col, (size_t)A.ptr[n]);
+  huge_reserve(A.val, (size_t)A.ptr[n]);
   A.col.resize(A.ptr[n]);
   A.val.resize(A.ptr[n]);
 #pragma omp parallel for schedule(static)
@@ -343,6 +349,8 @@ static void spgemm(const Csr& A, const Csr& B, Csr& C) {
     }
   }
   for (int64_t i = 0; i < n; ++i) C.ptr[i + 1] += C.ptr[i];
+  huge_reserve(C.col, (size_t)C.ptr[n]);
+  huge_reserve(C.val, (size_t)C.ptr[n]);
   C.col.resize(C.ptr[n]);
   C.val.resize(C.ptr[n]);
 #pragma omp parallel num_threads(nt)
@@ -375,6 +383,8 @@ static void transpose(const Csr& A, Csr& T) {
   T.ncols = A.nrows;
   const int64_t nc = A.ncols, nr = A.nrows;
   T.ptr.assign(nc + 1, 0);
+  huge_reserve(T.col, (size_t)A.nnz());
+  huge_reserve(T.val, (size_t)A.nnz());
   T.col.resize(A.nnz());
   T.val.resize(A.nnz());
   int nt = omp_get_max_threads();
@@ -445,6 +455,7 @@ struct OwnIndex {
 static void build_own_index(const std::vector<int32_t>& owner, int32_t nparts, OwnIndex& oi) {
   const int64_t n = (int64_t)owner.size();
   oi.own.assign(nparts, {});
+  huge_reserve(oi.lid, (size_t)n);
   oi.lid.resize(n);
   const int nt = omp_get_max_threads();
   std::vector<std::vector<int64_t>> cnt(nt, std::vector<int64_t>(nparts, 0));
@@ -471,6 +482,7 @@ static void build_own_index(const std::vector<int32_t>& owner, int32_t nparts, O
       s += v;
     }
     if (s >= INT32_MAX) throw std::runtime_error("part too large for int32 local ids");
+    huge_reserve(oi.own[p], (size_t)s);
     oi.own[p].resize(s);
   }
 #pragma omp parallel num_threads(nt)
@@ -541,6 +553,7 @@ static void aggregate_all(const Csr& M, const GpuMat* dM, const std::vector<int3
                           double eps, const std::vector<double>& absdiag, std::vector<int32_t>& agg_gid,
                           std::vector<int64_t>& counts, bool* on_gpu) {
   const int64_t n = M.nrows;
+  huge_reserve(agg_gid, (size_t)n);
   agg_gid.resize(n);
   counts.assign(nparts, 0);
   *on_gpu = false;
@@ -619,6 +632,8 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
       dnew[i] = dii + (dc - dii);  // same arithmetic as the oracle's A_F + diags(dF_new - d0)
     }
     for (int64_t i = 0; i < n; ++i) AF.ptr[i + 1] += AF.ptr[i];
+    huge_reserve(AF.col, (size_t)AF.ptr[n]);
+    huge_reserve(AF.val, (size_t)AF.ptr[n]);
     AF.col.resize(AF.ptr[n]);
     AF.val.resize(AF.ptr[n]);
 #pragma omp parallel for schedule(static)
@@ -693,6 +708,8 @@ static void build_prolongator(const Csr& A, const Csr& P0, int64_t nc, double ep
     P.ptr[i + 1] = cnt + (pe - pk);
   }
   for (int64_t i = 0; i < n; ++i) P.ptr[i + 1] += P.ptr[i];
+  huge_reserve(P.col, (size_t)P.ptr[n]);
+  huge_reserve(P.val, (size_t)P.ptr[n]);
   P.col.resize(P.ptr[n]);
   P.val.resize(P.ptr[n]);
 #pragma omp parallel for schedule(static)
@@ -949,6 +966,7 @@ static void split_blocks(const Csr& M, const std::vector<int64_t>& rows, const s
   oo.nrows = og.nrows = nr;
   oo.ncols = n_own_c;
   og.ncols = n_ghost_c;
+  huge_reserve(oo.ptr, (size_t)nr + 1);
   oo.ptr.assign(nr + 1, 0);
   og.ptr.assign(nr + 1, 0);
 #pragma omp parallel for schedule(static)
@@ -964,6 +982,8 @@ static void split_blocks(const Csr& M, const std::vector<int64_t>& rows, const s
     og.ptr[r + 1] += og.ptr[r];
   }
   if (oo.ptr[nr] > INT32_MAX || og.ptr[nr] > INT32_MAX) throw std::runtime_error("block nnz exceeds int32");
+  huge_reserve(oo.col, (size_t)oo.ptr[nr]);
+  huge_reserve(oo.val, (size_t)oo.ptr[nr]);
   oo.col.resize(oo.ptr[nr]);
   oo.val.resize(oo.ptr[nr]);
   og.col.resize(og.ptr[nr]);
@@ -1152,6 +1172,7 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
     int64_t nc = 0;
     int kdof = 1;
     bool agg_on_gpu = false;
+    huge_reserve(cur.agg_loc, (size_t)n);
     cur.agg_loc.resize(n);
     if (!use_ns) {
       aggregate_all(cur.A(), dA, cur.owner, cur.oi, nparts, eps, absdiag, agg_gid, counts, &agg_on_gpu);
@@ -1160,6 +1181,9 @@ void build_hierarchy(const Csr& A0, const std::vector<int32_t>& owner0, int32_t 
       if (nc >= n) break;
       P0.nrows = n;
       P0.ncols = nc;
+      huge_reserve(P0.ptr, (size_t)n + 1);
+      huge_reserve(P0.col, (size_t)n);
+      huge_reserve(P0.val, (size_t)n);
       P0.ptr.resize(n + 1);
       P0.col.resize(n);
       P0.val.assign(n, 1.0);

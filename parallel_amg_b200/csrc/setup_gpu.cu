@@ -243,7 +243,9 @@ GpuMat* gpu_upload(const Csr& A) {
   m->nrows = A.nrows;
   m->ncols = A.ncols;
   m->nnz = A.nnz();
-  std::vector<int32_t> col32(A.col.size());
+  std::vector<int32_t> col32;
+  huge_reserve(col32, A.col.size());
+  col32.resize(A.col.size());
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < (int64_t)A.col.size(); ++k) col32[k] = (int32_t)A.col[k];
   m->ptr.upload(A.ptr.data(), A.ptr.size());
@@ -255,10 +257,15 @@ GpuMat* gpu_upload(const Csr& A) {
 void gpu_download(const GpuMat* m, Csr& C) {
   C.nrows = m->nrows;
   C.ncols = m->ncols;
+  huge_reserve(C.ptr, (size_t)m->nrows + 1);
+  huge_reserve(C.col, (size_t)m->nnz);
+  huge_reserve(C.val, (size_t)m->nnz);
   C.ptr.resize(m->nrows + 1);
   C.col.resize(m->nnz);
   C.val.resize(m->nnz);
-  std::vector<int32_t> col32(m->nnz);
+  std::vector<int32_t> col32;
+  huge_reserve(col32, (size_t)m->nnz);
+  col32.resize(m->nnz);
   m->ptr.download(C.ptr.data(), (size_t)m->nrows + 1);
   if (m->nnz) {
     m->col.download(col32.data(), (size_t)m->nnz);
