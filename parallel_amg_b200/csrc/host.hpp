@@ -22,7 +22,7 @@ namespace pamg {
 // per 4 KB.  Where the kernel offers transparent huge pages on request (THP = madvise) a large buffer can be reserved first and
 // advised, so that the value-initialising resize / assign behind it faults in 2 MB steps.  MEASURED AND LEFT OFF: in the build
 // container 480 MB take 0.13-0.19 s instead of 0.31-0.42 s and the 160^3 host setup 4.1-4.9 s instead of 4.5-5.1 s, but on the GPU
-// box the 256^3 setup with the device chain went 8.96 -> 11.1 / 11.6 s (gpurun_out/r3_huge.log: the gallery halves, the phases
+// box the 256^3 setup with the device chain went 8.96 -> 11.1 / 11.6 s (profiles/r03_huge_pages.log: the gallery halves, the phases
 // that move matrices through pinned staging lose more).  PAMG_HUGE_PAGES=1 turns the hint on.
 inline bool huge_pages_wanted() {
   static const bool on = [] {
